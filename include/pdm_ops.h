@@ -1,0 +1,96 @@
+/*
+ * pdm_ops.h -- C ABI of libpdmops.so, the B200 (sm_100a) implementation of the
+ * PDM-SSD / OpenPCDet point-processing hot path.
+ *
+ * Every entry point takes plain device pointers + sizes + the CUDA stream to launch
+ * on (a cudaStream_t passed as void*; NULL = legacy default stream, which is what
+ * the reference launches on).  No torch types cross this boundary.  All tensors are
+ * dense, row-major ("contiguous" in torch terms), fp32 / int32, resident on the
+ * CURRENT CUDA device of the calling thread.  Outputs (and the FPS scratch `temp`)
+ * are allocated by the caller, exactly as in the reference (pointnet2_utils.py:25-26,
+ * 55,94-95,128,172,218); the library only writes into them.
+ *
+ * Return value: 0 on success, otherwise non-zero (a cudaError_t value, or
+ * PDM_ERR_* below); pdm_last_error() then returns a thread-local message.  The
+ * library never calls exit() (the reference does: sampling_gpu.cu:46-50).
+ *
+ * Each declaration cites the reference binding it replaces: the pybind entry in
+ * pcdet/ops/pointnet2/pointnet2_batch/src/pointnet2_api.cpp and the C++ wrapper
+ * behind it.  INTEGRATION.md shows the stub a pcdet maintainer adds to bind these.
+ */
+#ifndef PDM_OPS_H_
+#define PDM_OPS_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDM_OK 0
+#define PDM_ERR_INVALID_ARG (-1)   /* negative size, NULL pointer with non-empty tensor, ... */
+#define PDM_ERR_UNSUPPORTED (-2)   /* shape outside what the kernels implement */
+
+/* ABI version, bumped on any signature change. */
+int pdm_abi_version(void);
+/* Message for the last non-zero return on this thread ("" if none). */
+const char *pdm_last_error(void);
+/* Number of kernel launches issued by this library since load / since the last reset
+ * (bench.py reports it as gpu_launches). */
+long long pdm_launch_count(void);
+void pdm_reset_launch_count(void);
+
+/* ---- set-abstraction ops (reference: pointnet2_batch) ----------------------------- */
+
+/* farthest_point_sampling_wrapper (pointnet2_api.cpp:18, sampling.cpp:37-46,
+ * sampling_gpu.cu:100-260).  xyz (B,N,3) -> idx (B,M); temp (B,N) is caller scratch
+ * pre-filled with 1e10; on return it holds the running min distances exactly as the
+ * reference leaves them.  idx[:,0] = 0; ties resolved like the reference's
+ * block_size-dependent shared-memory tournament (DESIGN.md "FPS tie-break"). */
+int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                void *stream);
+
+/* gather_points_wrapper (pointnet2_api.cpp:16, sampling.cpp:14-23, sampling_gpu.cu:15-51).
+ * points (B,C,N), idx (B,M) -> out (B,C,M). */
+int pdm_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                      float *out, void *stream);
+
+/* gather_points_grad_wrapper (pointnet2_api.cpp:17, sampling.cpp:25-35, sampling_gpu.cu:53-91).
+ * grad_out (B,C,M), idx (B,M) -> grad_points (B,C,N) accumulated (+=). */
+int pdm_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                           float *grad_points, void *stream);
+
+/* ball_query_wrapper (pointnet2_api.cpp:13, ball_query.cpp:29-39, ball_query_gpu.cu:15-73).
+ * new_xyz (B,M,3), xyz (B,N,3) -> idx (B,M,nsample): first nsample indices k (ascending)
+ * with d2 < radius*radius, padded with the first hit; rows without a hit are left
+ * untouched (the caller zero-fills, pointnet2_utils.py:218). */
+int pdm_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                   const float *xyz, int *idx, void *stream);
+
+/* group_points_wrapper (pointnet2_api.cpp:14, group_points.cpp:27-37, group_points_gpu.cu:53-92).
+ * points (B,C,N), idx (B,npoints,nsample) -> out (B,C,npoints,nsample). */
+int pdm_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                     const int *idx, float *out, void *stream);
+
+/* group_points_grad_wrapper (pointnet2_api.cpp:15, group_points.cpp:15-25,
+ * group_points_gpu.cu:14-51).  grad_out (B,C,npoints,nsample) -> grad_points (B,C,N) (+=). */
+int pdm_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                          const int *idx, float *grad_points, void *stream);
+
+/* three_nn_wrapper (pointnet2_api.cpp:19, interpolate.cpp:18-27, interpolate_gpu.cu:16-81).
+ * unknown (B,N,3), known (B,M,3) -> dist2 (B,N,3) squared distances, idx (B,N,3). */
+int pdm_three_nn(int b, int n, int m, const float *unknown, const float *known, float *dist2,
+                 int *idx, void *stream);
+
+/* three_interpolate_wrapper (pointnet2_api.cpp:20, interpolate.cpp:29-42,
+ * interpolate_gpu.cu:84-124).  points (B,C,M), idx (B,N,3), weight (B,N,3) -> out (B,C,N). */
+int pdm_three_interpolate(int b, int c, int m, int n, const float *points, const int *idx,
+                          const float *weight, float *out, void *stream);
+
+/* three_interpolate_grad_wrapper (pointnet2_api.cpp:21, interpolate.cpp:44-56,
+ * interpolate_gpu.cu:127-169).  grad_out (B,C,N) -> grad_points (B,C,M) (+=). */
+int pdm_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                               const float *weight, float *grad_points, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDM_OPS_H_ */

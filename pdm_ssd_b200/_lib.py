@@ -1,0 +1,70 @@
+"""ctypes binding of libpdmops.so (the C ABI declared in include/pdm_ops.h).
+
+The product path has no CPU fallback: if the shared library is missing or does not
+export a symbol, importing/using the ops raises.  (`python -m pdm_ssd_b200.build`
+or `__graft_entry__.build()` produces the library; it is built in-tree.)
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libpdmops.so")
+
+_vp = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+
+# name -> argtypes, mirrors include/pdm_ops.h one to one
+SIGNATURES = {
+    "pdm_farthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "pdm_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pdm_gather_points_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pdm_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
+    "pdm_group_points": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pdm_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pdm_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pdm_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pdm_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+}
+
+_lib = None
+
+
+class PdmOpsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libpdmops.so once; raise loudly when it is absent or incomplete."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise PdmOpsError(
+            "libpdmops.so not found at %s -- build it with `python -m pdm_ssd_b200.build`; "
+            "there is deliberately no CPU fallback" % SO_PATH)
+    lib = ctypes.CDLL(SO_PATH)
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.argtypes = args
+        fn.restype = _i
+    lib.pdm_abi_version.restype = _i
+    lib.pdm_last_error.restype = ctypes.c_char_p
+    lib.pdm_launch_count.restype = ctypes.c_longlong
+    lib.pdm_reset_launch_count.restype = None
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().pdm_last_error().decode("utf-8", "replace")
+        raise PdmOpsError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+def launch_count():
+    return int(load().pdm_launch_count())
+
+
+def reset_launch_count():
+    load().pdm_reset_launch_count()

@@ -1,0 +1,38 @@
+// capi.cu -- error plumbing and bookkeeping behind include/pdm_ops.h.
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace pdm {
+
+thread_local char g_err[512] = {0};
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code == 0 ? PDM_ERR_INVALID_ARG : code;
+}
+
+// cuda_utils.h:10-14 of the reference, evaluated the same way (double log ratio, truncation).
+int ref_fps_block_size(int n) {
+    const int pow_2 = (int)(log((double)n) / log(2.0));
+    int v = 1 << pow_2;
+    if (v > 1024) v = 1024;
+    if (v < 1) v = 1;
+    return v;
+}
+
+}  // namespace pdm
+
+extern "C" {
+
+int pdm_abi_version(void) { return 1; }
+const char *pdm_last_error(void) { return pdm::g_err; }
+long long pdm_launch_count(void) { return pdm::g_launches.load(); }
+void pdm_reset_launch_count(void) { pdm::g_launches.store(0); }
+
+}  // extern "C"

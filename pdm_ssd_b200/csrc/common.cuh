@@ -1,0 +1,62 @@
+// common.cuh -- shared helpers for libpdmops (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+
+#include "../../include/pdm_ops.h"
+
+namespace pdm {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+int fail(int code, const char *fmt, ...);
+inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// Call right after a launch: returns non-zero (and records the message) on a launch error.
+#define PDM_CHECK_LAUNCH(what)                                                         \
+    do {                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess)                                                        \
+            return pdm::fail((int)e__, "%s: %s", what, cudaGetErrorString(e__));       \
+    } while (0)
+
+#define PDM_CHECK_CUDA(expr)                                                           \
+    do {                                                                               \
+        cudaError_t e__ = (expr);                                                      \
+        if (e__ != cudaSuccess)                                                        \
+            return pdm::fail((int)e__, "%s: %s", #expr, cudaGetErrorString(e__));      \
+    } while (0)
+
+// Squared distance with the reference's exact rounding sequence.  nvcc 12.9 contracts
+//   (ax-bx)*(ax-bx) + (ay-by)*(ay-by) + (az-bz)*(az-bz)
+// in sampling_gpu.cu:139, ball_query_gpu.cu:38 and interpolate_gpu.cu:41 into
+//   FMUL t = dy*dy ; FFMA t = dx*dx + t ; FFMA d = dz*dz + t
+// (read from the reference SASS).  Spelled with intrinsics so no optimisation
+// level or future compiler can re-associate it.
+__device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
+    return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// Streaming (evict-first) 128-bit store for write-once outputs.
+__device__ __forceinline__ void st_cs_f4(float *p, float4 v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_cs_f1(float *p, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// reference host helper cuda_utils.h:10-14 (block size the reference FPS would use);
+// decides the tie-break order our FPS has to reproduce.
+int ref_fps_block_size(int n);
+
+}  // namespace pdm

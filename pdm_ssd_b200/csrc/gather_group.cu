@@ -1,0 +1,157 @@
+// gather_group.cu -- index gathers of the set-abstraction path and their gradients.
+//
+//   gather_points : out[b,c,m]   = points[b,c,idx[b,m]]        (sampling_gpu.cu:15-31)
+//   group_points  : out[b,c,p,s] = points[b,c,idx[b,p,s]]      (group_points_gpu.cu:53-72)
+//
+// Both are pure copies, so results are bit-exact by construction.  They are bound by
+// the HBM write of `out` (group: 4*C*M*S bytes per frame); the reads are 4-byte random
+// gathers out of a (C,N) slab that is L2-resident.  Layout of the work: one thread owns
+// VEC=4 consecutive output columns j (16-byte index load, 16-byte streaming stores) and
+// walks a chunk of CH channels with all CH*VEC gathers issued before the first store,
+// so each thread keeps up to 32 independent L2 requests in flight.  The reference
+// re-reads idx once per channel (grid.y = C); here it is read once per CH channels.
+#include "common.cuh"
+
+namespace pdm {
+
+template <int CH>
+__global__ void __launch_bounds__(256)
+group_points_vec4_kernel(int c, int n, int cols4, const float *__restrict__ points,
+                         const int *__restrict__ idx, float *__restrict__ out) {
+    // grid: x = column quads, y = channel chunk, z = batch
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= cols4) return;
+    const int bi = blockIdx.z;
+    const int c0 = blockIdx.y * CH;
+    const size_t cols = (size_t)cols4 * 4;
+    const int4 id = __ldg(reinterpret_cast<const int4 *>(idx + (size_t)bi * cols) + q);
+    const float *src = points + ((size_t)bi * c + c0) * n;
+    float *dst = out + ((size_t)bi * c + c0) * cols + (size_t)q * 4;
+    float4 v[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        if (c0 + k < c) {
+            const float *s = src + (size_t)k * n;
+            v[k].x = __ldg(s + id.x);
+            v[k].y = __ldg(s + id.y);
+            v[k].z = __ldg(s + id.z);
+            v[k].w = __ldg(s + id.w);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+        if (c0 + k < c) st_cs_f4(dst + (size_t)k * cols, v[k]);
+    }
+}
+
+// Scalar variant for column counts that are not a multiple of 4 (or unaligned bases).
+template <int CH>
+__global__ void __launch_bounds__(256)
+group_points_scalar_kernel(int c, int n, size_t cols, const float *__restrict__ points,
+                           const int *__restrict__ idx, float *__restrict__ out) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    const int bi = blockIdx.z;
+    const int c0 = blockIdx.y * CH;
+    const int id = __ldg(idx + (size_t)bi * cols + j);
+    const float *src = points + ((size_t)bi * c + c0) * n;
+    float *dst = out + ((size_t)bi * c + c0) * cols + j;
+    float v[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+        if (c0 + k < c) v[k] = __ldg(src + (size_t)k * n + id);
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+        if (c0 + k < c) st_cs_f1(dst + (size_t)k * cols, v[k]);
+}
+
+// grad: grad_points[b,c,idx[b,j]] += grad_out[b,c,j]   (atomicAdd, as the reference:
+// group_points_gpu.cu:14-31, sampling_gpu.cu:53-70; summation order is unspecified there too)
+__global__ void __launch_bounds__(256)
+scatter_add_kernel(int c, int n, size_t cols, const float *__restrict__ grad_out,
+                   const int *__restrict__ idx, float *__restrict__ grad_points) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    const int bi = blockIdx.z, ci = blockIdx.y;
+    const int id = __ldg(idx + (size_t)bi * cols + j);
+    atomicAdd(grad_points + ((size_t)bi * c + ci) * n + id,
+              __ldg(grad_out + ((size_t)bi * c + ci) * cols + j));
+}
+
+static int launch_group(int b, int c, int n, size_t cols, const float *points, const int *idx,
+                        float *out, cudaStream_t st, const char *what) {
+    if (b < 0 || c < 0 || n < 0) return fail(PDM_ERR_INVALID_ARG, "%s: negative size", what);
+    if (b == 0 || c == 0 || cols == 0) return PDM_OK;
+    if (!points || !idx || !out) return fail(PDM_ERR_INVALID_ARG, "%s: null pointer", what);
+    if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "%s: batch %d > 65535", what, b);
+    constexpr int CH = 8;
+    const int chunks = (c + CH - 1) / CH;
+    if (chunks > 65535) return fail(PDM_ERR_UNSUPPORTED, "%s: too many channels %d", what, c);
+    const bool vec_ok = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    if (vec_ok) {
+        const int cols4 = (int)(cols / 4);
+        dim3 grid((cols4 + 255) / 256, chunks, b);
+        if (c >= CH)
+            group_points_vec4_kernel<CH><<<grid, 256, 0, st>>>(c, n, cols4, points, idx, out);
+        else {
+            grid.y = c;  // few channels: one per block row keeps registers low
+            group_points_vec4_kernel<1><<<grid, 256, 0, st>>>(c, n, cols4, points, idx, out);
+        }
+    } else {
+        dim3 grid((unsigned)((cols + 255) / 256), chunks, b);
+        group_points_scalar_kernel<CH><<<grid, 256, 0, st>>>(c, n, cols, points, idx, out);
+    }
+    count_launch();
+    PDM_CHECK_LAUNCH(what);
+    return PDM_OK;
+}
+
+static int launch_scatter_add(int b, int c, int n, size_t cols, const float *grad_out,
+                              const int *idx, float *grad_points, cudaStream_t st,
+                              const char *what) {
+    if (b < 0 || c < 0 || n < 0) return fail(PDM_ERR_INVALID_ARG, "%s: negative size", what);
+    if (b == 0 || c == 0 || cols == 0) return PDM_OK;
+    if (!grad_out || !idx || !grad_points) return fail(PDM_ERR_INVALID_ARG, "%s: null pointer", what);
+    if (b > 65535 || c > 65535) return fail(PDM_ERR_UNSUPPORTED, "%s: b/c > 65535", what);
+    dim3 grid((unsigned)((cols + 255) / 256), c, b);
+    scatter_add_kernel<<<grid, 256, 0, st>>>(c, n, cols, grad_out, idx, grad_points);
+    count_launch();
+    PDM_CHECK_LAUNCH(what);
+    return PDM_OK;
+}
+
+}  // namespace pdm
+
+extern "C" {
+
+int pdm_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,
+                      float *out, void *stream) {
+    if (npoints < 0) return pdm::fail(PDM_ERR_INVALID_ARG, "gather_points: negative size");
+    return pdm::launch_group(b, c, n, (size_t)npoints, points, idx, out, (cudaStream_t)stream,
+                             "gather_points");
+}
+
+int pdm_group_points(int b, int c, int n, int npoints, int nsample, const float *points,
+                     const int *idx, float *out, void *stream) {
+    if (npoints < 0 || nsample < 0) return pdm::fail(PDM_ERR_INVALID_ARG, "group_points: negative size");
+    return pdm::launch_group(b, c, n, (size_t)npoints * nsample, points, idx, out,
+                             (cudaStream_t)stream, "group_points");
+}
+
+int pdm_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                           float *grad_points, void *stream) {
+    if (npoints < 0) return pdm::fail(PDM_ERR_INVALID_ARG, "gather_points_grad: negative size");
+    return pdm::launch_scatter_add(b, c, n, (size_t)npoints, grad_out, idx, grad_points,
+                                   (cudaStream_t)stream, "gather_points_grad");
+}
+
+int pdm_group_points_grad(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                          const int *idx, float *grad_points, void *stream) {
+    if (npoints < 0 || nsample < 0)
+        return pdm::fail(PDM_ERR_INVALID_ARG, "group_points_grad: negative size");
+    return pdm::launch_scatter_add(b, c, n, (size_t)npoints * nsample, grad_out, idx, grad_points,
+                                   (cudaStream_t)stream, "group_points_grad");
+}
+
+}  // extern "C"

@@ -1,0 +1,246 @@
+"""GPU parity tests: our CUDA path (through the C ABI, via the reference-shaped Python API)
+against (1) the CPU oracle, (2) the committed golden vectors produced by the reference's
+kernels, (3) the reference's own compiled extension when oracle/_ref is present.
+Integer outputs must be bit-exact; float outputs of pure copies bit-exact too."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from pdm_ssd_b200 import _lib, pointnet2_utils as pu, pointnet2_batch_cuda as ours, synthetic
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def our_fps(xyz, m, return_temp=False):
+    x = _t(xyz)
+    B, N, _ = x.shape
+    temp = torch.full((B, N), 1e10, device=DEV)
+    idx = torch.full((B, m), -7, dtype=torch.int32, device=DEV)
+    ours.farthest_point_sampling_wrapper(B, N, m, x, temp, idx)
+    torch.cuda.synchronize()
+    return (idx.cpu().numpy(), temp.cpu().numpy()) if return_temp else idx.cpu().numpy()
+
+
+def test_library_is_native():
+    assert os.path.exists(_lib.SO_PATH)
+    assert _lib.load().pdm_abi_version() == 1
+
+
+# ------------------------------------------------------------------ FPS
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "fps_*.npz"))))
+def test_fps_golden(path):
+    g = np.load(path)
+    idx, temp = our_fps(g["xyz"], int(g["m"]), return_temp=True)
+    assert np.array_equal(idx, g["idx"]), os.path.basename(path)
+    assert np.array_equal(temp, g["temp"]), "running-min scratch differs from the reference's"
+
+
+def test_fps_golden_present(golden_dir):
+    assert len(glob.glob(os.path.join(golden_dir, "fps_*.npz"))) >= 8
+
+
+@pytest.mark.parametrize("n,m,kind", [
+    (512, 100, "uniform"), (700, 256, "uniform"), (1024, 1024, "uniform"), (1500, 300, "dups"),
+    (2048, 512, "kitti"), (3000, 1000, "uniform"), (4096, 1024, "kitti"), (5000, 50, "dups"),
+    (8192, 2048, "kitti"), (16384, 1024, "uniform"), (100, 100, "uniform"), (33, 7, "uniform"),
+    (1, 1, "uniform"), (2, 2, "uniform"), (511, 64, "dups"), (16385, 40, "uniform"),
+])
+def test_fps_vs_oracle(n, m, kind):
+    rng = np.random.default_rng(n * 7 + m)
+    if kind == "kitti":
+        xyz = synthetic.kitti_batch(3, n, first_frame=n % 11)[..., :3].copy()
+    else:
+        xyz = rng.uniform(-20, 20, (3, n, 3)).astype(np.float32)
+        if kind == "dups":
+            h = n // 3
+            xyz[:, -h:] = xyz[:, :h]
+    want, want_t = oracle.fps(xyz, m, return_temp=True)
+    got, got_t = our_fps(xyz, m, return_temp=True)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_t, want_t)
+
+
+def test_fps_full_size_properties():
+    """BASELINE size (16 x 16384 -> 4096): oracle on 2 frames, structural properties on all."""
+    frames = synthetic.kitti_batch(16)[..., :3].copy()
+    idx = our_fps(frames, 4096)
+    assert idx.shape == (16, 4096) and (idx[:, 0] == 0).all()
+    assert idx.min() >= 0 and idx.max() < 16384
+    want = oracle.fps(frames[:2], 4096)
+    assert np.array_equal(idx[:2], want)
+    for b in range(16):
+        # distinct coordinates are never sampled twice before all distinct points are used
+        pts = frames[b][idx[b]]
+        nuniq = len(np.unique(frames[b], axis=0))
+        assert len(np.unique(pts, axis=0)) == min(4096, nuniq)
+    # batch independence: frame 5 alone gives the same answer
+    assert np.array_equal(our_fps(frames[5:6], 4096)[0], idx[5])
+
+
+def test_fps_generic_kernel_matches(monkeypatch):
+    xyz = synthetic.kitti_batch(2, 4096)[..., :3].copy()
+    a = our_fps(xyz, 512)
+    monkeypatch.setenv("PDM_FPS_KERNEL", "generic")
+    b = our_fps(xyz, 512)
+    assert np.array_equal(a, b)
+
+
+def test_fps_vs_reference_extension(ref_ext):
+    if ref_ext is None:
+        pytest.skip("oracle/_ref not built")
+    for n, m in [(16384, 4096), (4096, 1024), (1000, 333)]:
+        xyz = _t(synthetic.kitti_batch(4, n, first_frame=20)[..., :3].copy())
+        t1 = torch.full((4, n), 1e10, device=DEV); i1 = torch.zeros((4, m), dtype=torch.int32, device=DEV)
+        t2 = torch.full((4, n), 1e10, device=DEV); i2 = torch.zeros((4, m), dtype=torch.int32, device=DEV)
+        ref_ext.farthest_point_sampling_wrapper(4, n, m, xyz, t1, i1)
+        ours.farthest_point_sampling_wrapper(4, n, m, xyz, t2, i2)
+        torch.cuda.synchronize()
+        assert torch.equal(i1, i2)
+        assert torch.equal(t1, t2)
+
+
+# ------------------------------------------------------------------ ball query
+def our_bq(radius, nsample, xyz, new_xyz):
+    return pu.ball_query(float(radius), int(nsample), _t(xyz), _t(new_xyz)).cpu().numpy()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "bq_*.npz"))))
+def test_ball_query_golden(path):
+    g = np.load(path)
+    got = our_bq(g["radius"], g["nsample"], g["xyz"], g["new_xyz"])
+    assert np.array_equal(got, g["idx"]), os.path.basename(path)
+
+
+@pytest.mark.parametrize("n,m,r,s", [(4096, 1024, 0.8, 32), (4096, 1024, 1.6, 16), (1000, 37, 2.5, 64),
+                                     (16384, 4096, 0.8, 32), (300, 300, 0.05, 4), (129, 1, 100.0, 200)])
+def test_ball_query_vs_oracle(n, m, r, s):
+    fr = synthetic.kitti_batch(2, n, first_frame=n % 5)[..., :3].copy()
+    cidx = oracle.fps(fr, m)
+    new_xyz = np.take_along_axis(fr, cidx[..., None].astype(np.int64).repeat(3, -1), 1)
+    assert np.array_equal(our_bq(r, s, fr, new_xyz), oracle.ball_query(r, s, fr, new_xyz))
+
+
+def test_ball_query_leaves_rows_without_hits_untouched():
+    xyz = _t(np.random.default_rng(0).uniform(0, 1, (1, 50, 3)).astype(np.float32))
+    q = _t(np.full((1, 4, 3), 50.0, np.float32))
+    idx = torch.full((1, 4, 6), 1234, dtype=torch.int32, device=DEV)
+    ours.ball_query_wrapper(1, 50, 4, 0.5, 6, q, xyz, idx)
+    assert (idx == 1234).all()
+
+
+# ------------------------------------------------------------------ group / gather
+@pytest.mark.parametrize("B,C,N,M,S", [(2, 3, 4096, 1024, 32), (2, 64, 4096, 1024, 32), (3, 1, 16384, 512, 32),
+                                       (1, 5, 100, 7, 3), (2, 17, 333, 41, 5), (1, 8, 64, 1, 1)])
+def test_group_and_gather(B, C, N, M, S):
+    rng = np.random.default_rng(B * 100 + C)
+    pts = rng.normal(0, 1, (B, C, N)).astype(np.float32)
+    idx = rng.integers(0, N, (B, M, S)).astype(np.int32)
+    got = pu.grouping_operation(_t(pts), _t(idx)).cpu().numpy()
+    assert np.array_equal(got, oracle.group_points(pts, idx))
+    g1 = pu.gather_operation(_t(pts), _t(idx[:, :, 0].copy())).cpu().numpy()
+    assert np.array_equal(g1, oracle.gather_points(pts, idx[:, :, 0].copy()))
+
+
+def test_group_gather_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "group_gather.npz"))
+    assert np.array_equal(pu.grouping_operation(_t(g["points"]), _t(g["idx"])).cpu().numpy(), g["grouped"])
+    assert np.array_equal(pu.gather_operation(_t(g["points"]), _t(g["idx"][:, :, 0].copy())).cpu().numpy(),
+                          g["gathered"])
+
+
+def test_group_gather_grads_match_oracle():
+    rng = np.random.default_rng(3)
+    pts = torch.tensor(rng.normal(0, 1, (2, 4, 200)).astype(np.float32), device=DEV, requires_grad=True)
+    idx = rng.integers(0, 200, (2, 30, 6)).astype(np.int32)
+    go = rng.normal(0, 1, (2, 4, 30, 6)).astype(np.float32)
+    out = pu.grouping_operation(pts, _t(idx))
+    out.backward(_t(go))
+    np.testing.assert_allclose(pts.grad.cpu().numpy(), oracle.group_points_grad(go, idx, 200), rtol=1e-5, atol=1e-5)
+    pts.grad = None
+    out = pu.gather_operation(pts, _t(idx[:, :, 0].copy()))
+    out.backward(_t(go[:, :, :, 0].copy()))
+    np.testing.assert_allclose(pts.grad.cpu().numpy(),
+                               oracle.gather_points_grad(go[:, :, :, 0].copy(), idx[:, :, 0].copy(), 200),
+                               rtol=1e-5, atol=1e-5)
+
+
+# ------------------------------------------------------------------ three_nn / interpolate
+def test_interp_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "interp_n500_m77.npz"))
+    B, n, _ = g["unknown"].shape
+    m = g["known"].shape[1]
+    d2 = torch.zeros((B, n, 3), device=DEV); ni = torch.zeros((B, n, 3), dtype=torch.int32, device=DEV)
+    ours.three_nn_wrapper(B, n, m, _t(g["unknown"]), _t(g["known"]), d2, ni)
+    assert np.array_equal(ni.cpu().numpy(), g["idx"])
+    assert np.array_equal(d2.cpu().numpy(), g["dist2"])
+    out = pu.three_interpolate(_t(g["feats"]), _t(g["idx"]), _t(g["weight"])).cpu().numpy()
+    assert np.array_equal(out, g["out"])
+    g2 = np.load(os.path.join(golden_dir, "three_nn_m2.npz"))
+    d2 = torch.zeros((1, 4, 3), device=DEV); ni = torch.zeros((1, 4, 3), dtype=torch.int32, device=DEV)
+    ours.three_nn_wrapper(1, 4, 2, _t(g2["unknown"]), _t(g2["known"]), d2, ni)
+    assert np.array_equal(ni.cpu().numpy(), g2["idx"]) and np.array_equal(d2.cpu().numpy(), g2["dist2"])
+
+
+@pytest.mark.parametrize("B,n,m,C", [(2, 1024, 256, 16), (1, 3000, 1500, 3), (2, 77, 5, 9), (1, 10, 1, 2)])
+def test_three_nn_interpolate_vs_oracle(B, n, m, C):
+    rng = np.random.default_rng(n + m)
+    unk = rng.uniform(0, 10, (B, n, 3)).astype(np.float32)
+    kn = rng.uniform(0, 10, (B, m, 3)).astype(np.float32)
+    feats = rng.normal(0, 1, (B, C, m)).astype(np.float32)
+    want_d2, want_i = oracle.three_nn(unk, kn)
+    dist, idx = pu.three_nn(_t(unk), _t(kn))
+    assert np.array_equal(idx.cpu().numpy(), want_i)
+    assert np.array_equal(dist.cpu().numpy(), np.sqrt(want_d2))
+    w = rng.uniform(0, 1, (B, n, 3)).astype(np.float32)
+    got = pu.three_interpolate(_t(feats), _t(want_i), _t(w)).cpu().numpy()
+    assert np.array_equal(got, oracle.three_interpolate(feats, want_i, w))
+    f = torch.tensor(feats, device=DEV, requires_grad=True)
+    go = rng.normal(0, 1, (B, C, n)).astype(np.float32)
+    pu.three_interpolate(f, _t(want_i), _t(w)).backward(_t(go))
+    np.testing.assert_allclose(f.grad.cpu().numpy(), oracle.three_interpolate_grad(go, want_i, w, m),
+                               rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------ whole-op reference extension
+def test_all_ops_vs_reference_extension(ref_ext):
+    if ref_ext is None:
+        pytest.skip("oracle/_ref not built")
+    fr = _t(synthetic.kitti_batch(2, 4096, first_frame=9)[..., :3].copy())
+    feats = torch.randn(2, 32, 4096, device=DEV)
+    res = []
+    for be in (ours, ref_ext):
+        with pu.use_backend(be):
+            fi = pu.farthest_point_sample(fr, 1024)
+            new_xyz = pu.gather_operation(fr.transpose(1, 2).contiguous(), fi).transpose(1, 2).contiguous()
+            grp = pu.QueryAndGroup(1.6, 32)(fr, new_xyz, feats)
+            dist, ni = pu.three_nn(fr, new_xyz)
+            w = 1.0 / (dist + 1e-8)
+            w = (w / w.sum(2, keepdim=True)).contiguous()
+            itp = pu.three_interpolate(grp[:, :, :, 0].contiguous(), ni, w)
+            res.append((fi, new_xyz, grp, dist, ni, itp))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------ error behaviour
+def test_errors_raise_instead_of_exit():
+    x = torch.zeros((1, 8, 3), device=DEV)
+    with pytest.raises(RuntimeError):
+        ours.farthest_point_sampling_wrapper(1, 8, 4, x.cpu(), torch.zeros(1, 8), torch.zeros(1, 4, dtype=torch.int32))
+    with pytest.raises(RuntimeError):
+        ours.farthest_point_sampling_wrapper(1, 8, 4, x, torch.zeros((1, 8), device=DEV),
+                                             torch.zeros((1, 4), dtype=torch.int64, device=DEV))
+    with pytest.raises(RuntimeError):
+        ours.ball_query_wrapper(1, 8, 2, 0.5, 4, x[:, :2].transpose(1, 2), x, torch.zeros((1, 2, 4), dtype=torch.int32, device=DEV))
+    with pytest.raises(_lib.PdmOpsError):
+        ours.farthest_point_sampling_wrapper(1, 0, 4, x[:, :0].contiguous(), torch.zeros((1, 0), device=DEV),
+                                             torch.zeros((1, 4), dtype=torch.int32, device=DEV))
