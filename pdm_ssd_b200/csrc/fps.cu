@@ -28,6 +28,8 @@
 //   instead of a sweep over all n points.  Running minima live in registers, coordinates in
 //   shared memory (SoA, conflict-free), the argmax uses redux.sync and one barrier/round.
 // fps_generic_kernel: any n; same key trick, temp in global memory.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pdm {
@@ -117,26 +119,89 @@ template <int NW, int BPW>
 struct FpsSmem {
     static constexpr int CAP = NW * BPW * 32;
     // [0, 12*CAP): sx, sy, sz (aliased by the 8*CAP-byte sort keys during set-up)
-    // then pub[2][NW] uint4, then 8 floats of frame box scratch per warp
+    // then pub[2][NW] uint2 (value bits, position), pubtk[2][NW] tiekeys, frame-box scratch
     static constexpr size_t kPubOff = (size_t)12 * CAP;
-    static constexpr size_t kBoxOff = kPubOff + sizeof(uint4) * 2 * NW;
+    static constexpr size_t kTkOff = kPubOff + sizeof(uint2) * 2 * NW;
+    static constexpr size_t kBoxOff = kTkOff + sizeof(unsigned) * 2 * NW;
     static constexpr size_t kBytes = kBoxOff + sizeof(float) * 6 * NW;
 };
 
-template <int NW, int BPW>
+// Critical-path idiom (latencies measured on B200, tools/micro/lat.cu): a warp argmax that also
+// needs a payload of the winning lane costs  redux(28) + redux(27) = 55 cycles as
+//     mx = redux.max(v);  payload = redux.max(v == mx ? payload : 0)
+// against 108 for redux + ballot + ffs + shfl.  The payload form is only valid when exactly one
+// lane holds the maximum; equal maxima (duplicate points) are detected with a ballot that runs
+// off the critical path and resolved by the smallest tiekey in a slow path.
+__device__ __forceinline__ bool multi_bit(unsigned ball) { return (ball & (ball - 1u)) != 0u; }
+
+// t[jj] for a warp-uniform runtime jj, with t[] in registers.  A 32-way switch around the
+// whole bucket update thrashed the instruction cache (20 KB loop), a flat 32-way select tree
+// costs ~95 half-rate ALU instructions.  So: groups of 8 registers; a (uniform) 2-level branch
+// picks the group, a 3-level select tree (7 FSEL) picks the register inside it.
+template <int W>
+__device__ __forceinline__ float reg_select_tree(const float *t, int jj) {
+    float a[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) a[i] = t[i];
+#pragma unroll
+    for (int bit = 0; (1 << bit) < W; ++bit) {
+        const bool odd = (jj >> bit) & 1;
+#pragma unroll
+        for (int i = 0; i < (W >> (bit + 1)); ++i) a[i] = odd ? a[2 * i + 1] : a[2 * i];
+    }
+    return a[0];
+}
+template <int BPW>
+__device__ __forceinline__ float reg_select(const float (&t)[BPW], int jj) {
+    if constexpr (BPW <= 8) {
+        return reg_select_tree<BPW>(t, jj);
+    } else {
+        switch (jj >> 3) {
+            case 0: return reg_select_tree<8>(&t[0], jj & 7);
+            case 1: return reg_select_tree<8>(&t[8], jj & 7);
+            case 2: if constexpr (BPW > 16) return reg_select_tree<8>(&t[16], jj & 7);
+            default: if constexpr (BPW > 24) return reg_select_tree<8>(&t[24], jj & 7);
+        }
+        return 0.f;
+    }
+}
+template <int BPW>
+__device__ __forceinline__ void reg_store(float (&t)[BPW], int jj, float v) {
+    if constexpr (BPW <= 8) {
+#pragma unroll
+        for (int q = 0; q < BPW; ++q) t[q] = (q == jj) ? v : t[q];
+    } else {
+        const int r = jj & 7;
+        switch (jj >> 3) {
+#define PDM_GRP(G)                                                         \
+    case G:                                                                \
+        if constexpr (BPW > 8 * G) {                                       \
+            _Pragma("unroll") for (int q = 0; q < 8; ++q) t[8 * G + q] = (q == r) ? v : t[8 * G + q]; \
+        }                                                                  \
+        break;
+            PDM_GRP(0) PDM_GRP(1) PDM_GRP(2) PDM_GRP(3)
+#undef PDM_GRP
+            default: break;
+        }
+    }
+}
+
+// PROF: debug build that accumulates clock64() per phase and per warp into `prof`
+// ([frame][warp][8] = A, B, C, barrier wait, D cycles, #bucket updates, #C runs, total).
+template <int NW, int BPW, bool PROF = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__restrict__ temp,
-                  int *__restrict__ idxs) {
+                  int *__restrict__ idxs, long long *__restrict__ prof = nullptr) {
     using L = FpsSmem<NW, BPW>;
     constexpr int CAP = L::CAP;
     constexpr int T = NW * 32;
-    static_assert(BPW <= 32, "one lane per owned bucket");
+    static_assert(BPW <= 32 && NW <= 32, "one lane per owned bucket / per warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sx = reinterpret_cast<float *>(smem_raw);
     float *sy = sx + CAP;
     float *sz = sy + CAP;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
-    uint4 *pub = reinterpret_cast<uint4 *>(smem_raw + L::kPubOff);
+    uint2 *pub = reinterpret_cast<uint2 *>(smem_raw + L::kPubOff);
     float *box = reinterpret_cast<float *>(smem_raw + L::kBoxOff);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -171,15 +236,12 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
         }
     }
     __syncthreads();
-    {
-        float l2[3], h2[3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            l2[a] = lane < NW ? box[lane * 6 + a] : INFINITY;
-            h2[a] = lane < NW ? box[lane * 6 + 3 + a] : -INFINITY;
-            lo[a] = ord2f(__reduce_min_sync(kFull, f2ord(l2[a])));
-            hi[a] = ord2f(__reduce_max_sync(kFull, f2ord(h2[a])));
-        }
+    for (int a = 0; a < 3; ++a) {
+        const float l2 = lane < NW ? box[lane * 6 + a] : INFINITY;
+        const float h2 = lane < NW ? box[lane * 6 + 3 + a] : -INFINITY;
+        lo[a] = ord2f(__reduce_min_sync(kFull, f2ord(l2)));
+        hi[a] = ord2f(__reduce_max_sync(kFull, f2ord(h2)));
     }
     const float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
     const float inv = (ext > 0.f && ext < INFINITY) ? 1023.0f / ext : 0.f;
@@ -219,34 +281,36 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
     }
 
     // ---- 3. distribute: lane owns slot `lane` of buckets  b = j*NW + w --------------------
-    unsigned tk[BPW];   // tiekey of my point in owned bucket j (kPadKey for padding)
-    float t[BPW];       // its running min distance
+    // Sorted position pos = b*32 + lane.  Padding keys sort last, so pos >= n <=> padding.
+    // The caller's scratch `temp` doubles as the pos -> original-index map while the kernel
+    // runs (read back only for the output index and for tie-breaks); step 5 restores it.
+    float t[BPW];       // running min distance of my point in owned bucket j
     unsigned kk_[BPW];
 #pragma unroll
-    for (int j = 0; j < BPW; ++j) kk_[j] = (unsigned)keys[((j * NW + w) << 5) + lane];  // low 32 bits = k
+    for (int j = 0; j < BPW; ++j) kk_[j] = (unsigned)keys[((j * NW + w) << 5) + lane];  // low word = k
+    __syncthreads();  // keys are dead from here on; the region becomes sx/sy/sz
 #pragma unroll
     for (int j = 0; j < BPW; ++j) {
-        // padding keys are ~0 -> low word 0xffffffff
-        const bool pad = keys[((j * NW + w) << 5) + lane] == ~0ull;
-        tk[j] = pad ? kPadKey : fps_tiekey(kk_[j], p, bsmask);
+        const int pos = ((j * NW + w) << 5) + lane;
+        t[j] = pos < n ? tmp[kk_[j]] : 0.f;   // padding: 0 and never the tie winner
     }
-    __syncthreads();  // keys are dead from here on; the region becomes sx/sy/sz
+    __syncthreads();  // every initial temp value is read before the map overwrites the buffer
+    unsigned *pmap = reinterpret_cast<unsigned *>(tmp);
 
     // per-bucket state, held by lane j of the owning warp
     float blox = INFINITY, bloy = INFINITY, bloz = INFINITY;
     float bhix = -INFINITY, bhiy = -INFINITY, bhiz = -INFINITY;
-    unsigned bmax = 0u, btk = kPadKey, bwl = 0u;
+    unsigned bmax = 0u, bwl = 0u;
 #pragma unroll
     for (int j = 0; j < BPW; ++j) {
         const int pos = ((j * NW + w) << 5) + lane;
-        const bool pad = tk[j] == kPadKey;
+        const bool pad = pos >= n;
         float x = 0.f, y = 0.f, z = 0.f;
-        t[j] = 0.f;
         if (!pad) {
             x = __ldg(dataset + kk_[j] * 3 + 0);
             y = __ldg(dataset + kk_[j] * 3 + 1);
             z = __ldg(dataset + kk_[j] * 3 + 2);
-            t[j] = tmp[kk_[j]];
+            pmap[pos] = kk_[j];
         }
         sx[pos] = x;
         sy[pos] = y;
@@ -262,81 +326,129 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
         const unsigned hz = __reduce_max_sync(kFull, oz ? 0u : f2ord(z));
         const unsigned tb = __float_as_uint(t[j]);
         const unsigned mx = __reduce_max_sync(kFull, tb);
-        const unsigned cand = (tb == mx) ? tk[j] : kPadKey;
+        const unsigned cand = (tb == mx && !pad) ? fps_tiekey(kk_[j], p, bsmask) : kPadKey;
         const unsigned tkm = __reduce_min_sync(kFull, cand);
         const unsigned wl = __ffs(__ballot_sync(kFull, cand == tkm)) - 1;
         if (lane == j) {
             blox = ord2f(lx); bloy = ord2f(ly); bloz = ord2f(lz);
             bhix = ord2f(hx); bhiy = ord2f(hy); bhiz = ord2f(hz);
-            bmax = mx; btk = tkm; bwl = wl;
+            bmax = mx; bwl = wl;
         }
     }
     __syncthreads();
 
     // ---- 4. rounds -------------------------------------------------------------------------
     float cx = __ldg(dataset + 0), cy = __ldg(dataset + 1), cz = __ldg(dataset + 2);  // sample 0 = point 0
-    unsigned wm = 0u, wtk = kPadKey, wpos = 0u;  // cached best of this warp
+    unsigned wm = 0u, wpos = 0u;  // cached best of this warp (value bits, sorted position)
     bool dirty = true;
+    const int wbase = (w << 5) + lane;                               // my slot in owned bucket 0
+    const unsigned bbase = (unsigned)(lane * (NW * 32) + (w << 5));  // first slot of owned bucket `lane`
+    // tiekey of the point at sorted position pos (global read: slow paths only)
+    auto tiekey_at = [&](unsigned pos) -> unsigned {
+        return pos < (unsigned)n ? fps_tiekey(pmap[pos], p, bsmask) : kPadKey;
+    };
+    unsigned pending = 0u;  // thread 0: original index of the previous round's winner (in flight)
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tq = 0, tq0 = 0;
+    if (PROF) tq0 = tq = clock64();
+#define PDM_TICK(SLOT)                         \
+    if (PROF) {                                \
+        const long long now = clock64();       \
+        pc[SLOT] += now - tq;                  \
+        tq = now;                              \
+    }
     for (int j = 1; j < m; ++j) {
-        // A. which of my buckets can change?
-        bool act = false;
-        if (lane < BPW) {
-            const float gx = fmaxf(fmaxf(__fsub_rn(blox, cx), __fsub_rn(cx, bhix)), 0.f);
-            const float gy = fmaxf(fmaxf(__fsub_rn(bloy, cy), __fsub_rn(cy, bhiy)), 0.f);
-            const float gz = fmaxf(fmaxf(__fsub_rn(bloz, cz), __fsub_rn(cz, bhiz)), 0.f);
-            act = sqdist_ref(gx, gy, gz) < __uint_as_float(bmax);
-        }
-        const unsigned mask = __ballot_sync(kFull, act);
-        // B. update the surviving buckets (warp-uniform branches, static register indices)
-        if (mask) {
-            dirty = true;
-#pragma unroll
-            for (int jj = 0; jj < BPW; ++jj) {
-                if (mask & (1u << jj)) {
-                    const int pos = ((jj * NW + w) << 5) + lane;
-                    const float d = sqdist_ref(__fsub_rn(sx[pos], cx), __fsub_rn(sy[pos], cy),
-                                               __fsub_rn(sz[pos], cz));
-                    const float nt = fminf(d, t[jj]);
-                    t[jj] = nt;
-                    const unsigned tb = __float_as_uint(nt);
-                    const unsigned mx = __reduce_max_sync(kFull, tb);
-                    const unsigned cand = (tb == mx) ? tk[jj] : kPadKey;
-                    const unsigned tkm = __reduce_min_sync(kFull, cand);
-                    const unsigned wl = __ffs(__ballot_sync(kFull, cand == tkm)) - 1;
-                    if (lane == jj) { bmax = mx; btk = tkm; bwl = wl; }
-                }
+        // A. which of my buckets can change?  exact lower bound of d over the bucket box
+        // (lanes >= BPW hold an empty box: gap = +inf, never active -- no divergent branch needed)
+        const float gx = fmaxf(fmaxf(__fsub_rn(blox, cx), __fsub_rn(cx, bhix)), 0.f);
+        const float gy = fmaxf(fmaxf(__fsub_rn(bloy, cy), __fsub_rn(cy, bhiy)), 0.f);
+        const float gz = fmaxf(fmaxf(__fsub_rn(bloz, cz), __fsub_rn(cz, bhiz)), 0.f);
+        unsigned mask = __ballot_sync(kFull, sqdist_ref(gx, gy, gz) < __uint_as_float(bmax));
+        PDM_TICK(0)
+        // B. update the surviving buckets, one 32-point bucket per iteration
+        while (mask) {
+            const int jj = 31 - __clz(mask);
+            mask ^= 1u << jj;
+            const int pos = jj * (NW * 32) + wbase;
+            const float d = sqdist_ref(__fsub_rn(sx[pos], cx), __fsub_rn(sy[pos], cy), __fsub_rn(sz[pos], cz));
+            const float nt = fminf(d, reg_select<BPW>(t, jj));
+            const unsigned tb = __float_as_uint(nt);
+            const unsigned mx = __reduce_max_sync(kFull, tb);
+            const bool hit = tb == mx;
+            unsigned wl = __reduce_max_sync(kFull, hit ? (unsigned)lane : 0u);
+            if (multi_bit(__ballot_sync(kFull, hit))) {  // duplicates: smallest tiekey wins
+                const unsigned cand = hit ? tiekey_at(pos) : kPadKey;
+                const unsigned tkm = __reduce_min_sync(kFull, cand);
+                wl = __reduce_max_sync(kFull, cand == tkm ? (unsigned)lane : 0u);
             }
+            if (lane == jj) { bmax = mx; bwl = wl; }
+            reg_store<BPW>(t, jj, nt);
+            dirty = true;
+            if (PROF) pc[5] += 1;
         }
-        // C. block argmax over bucket maxima
+        PDM_TICK(1)
+        // C. best of this warp (only when one of its buckets changed)
         if (dirty) {
             dirty = false;
             const unsigned v = lane < BPW ? bmax : 0u;
             wm = __reduce_max_sync(kFull, v);
-            const unsigned c2 = (lane < BPW && v == wm) ? btk : kPadKey;
-            wtk = __reduce_min_sync(kFull, c2);
-            const int src = __ffs(__ballot_sync(kFull, c2 == wtk)) - 1;  // lane 0 if nothing but padding
-            const unsigned sl = __shfl_sync(kFull, bwl, src);
-            wpos = (((unsigned)src * NW + w) << 5) + sl;
+            const bool hit = lane < BPW && v == wm;
+            wpos = __reduce_max_sync(kFull, hit ? bbase + bwl : 0u);
+            if (multi_bit(__ballot_sync(kFull, hit))) {  // several buckets share the maximum
+                const unsigned c2 = hit ? tiekey_at(bbase + bwl) : kPadKey;
+                const unsigned tkm = __reduce_min_sync(kFull, c2);
+                wpos = __reduce_max_sync(kFull, (hit && c2 == tkm) ? bbase + bwl : 0u);
+            }
+            if (PROF) pc[6] += 1;
         }
-        if (lane == 0) pub[(j & 1) * NW + w] = make_uint4(wm, wtk, wpos, 0u);
+        PDM_TICK(2)
+        const int par = (j & 1) * NW;
+        if (lane == 0) pub[par + w] = make_uint2(wm, wpos);
         __syncthreads();
-        uint4 e = make_uint4(0u, kPadKey, 0u, 0u);
-        if (lane < NW) e = pub[(j & 1) * NW + lane];
+        PDM_TICK(3)
+        // D. block argmax (every warp redundantly: no second barrier)
+        uint2 e = make_uint2(0u, 0u);
+        if (lane < NW) e = pub[par + lane];
         const unsigned gm = __reduce_max_sync(kFull, e.x);
-        const unsigned c3 = (e.x == gm) ? e.y : kPadKey;
-        const unsigned gtk = __reduce_min_sync(kFull, c3);
-        const int srcw = __ffs(__ballot_sync(kFull, c3 == gtk)) - 1;
-        const unsigned gpos = __shfl_sync(kFull, e.z, srcw);
+        const bool ghit = lane < NW && e.x == gm;
+        unsigned gpos = __reduce_max_sync(kFull, ghit ? e.y : 0u);
+        if (multi_bit(__ballot_sync(kFull, ghit))) {  // several warps share the maximum
+            const unsigned c3 = ghit ? tiekey_at(e.y) : kPadKey;
+            const unsigned gtk = __reduce_min_sync(kFull, c3);
+            gpos = __reduce_max_sync(kFull, (ghit && c3 == gtk) ? e.y : 0u);
+        }
         cx = sx[gpos];
         cy = sy[gpos];
         cz = sz[gpos];
-        if (tid == 0) out[j] = (int)fps_tiekey_inv(gtk, p, bsmask);
+        // output index: software-pipelined so the global read of the map never stalls a round
+        if (tid == 0) {
+            if (j > 1) out[j - 1] = (int)pending;
+            pending = pmap[gpos];
+        }
+        if (PROF) { cx += 0.f * __uint_as_float(gpos); }  // keep the loads inside the D window
+        PDM_TICK(4)
+    }
+    if (tid == 0) out[m - 1] = (int)pending;
+#undef PDM_TICK
+    if (PROF && lane == 0 && prof) {
+        pc[7] = clock64() - tq0;
+        for (int q = 0; q < 8; ++q) prof[((size_t)blockIdx.x * NW + w) * 8 + q] = pc[q];
     }
 
-    // ---- 5. leave temp as the reference does ---------------------------------------------
+    // ---- 5. leave temp as the reference does: running minima in original order ------------
+    __syncthreads();
+    unsigned ko[BPW];
 #pragma unroll
-    for (int j = 0; j < BPW; ++j)
-        if (tk[j] != kPadKey) tmp[fps_tiekey_inv(tk[j], p, bsmask)] = t[j];
+    for (int j = 0; j < BPW; ++j) {
+        const int pos = ((j * NW + w) << 5) + lane;
+        ko[j] = pos < n ? pmap[pos] : 0u;
+    }
+    __syncthreads();  // all map entries are read before any of them is overwritten
+#pragma unroll
+    for (int j = 0; j < BPW; ++j) {
+        const int pos = ((j * NW + w) << 5) + lane;
+        if (pos < n) tmp[ko[j]] = t[j];
+    }
 }
 
 template <int NW, int BPW>
@@ -346,13 +458,57 @@ static int launch_bucket(int b, int n, int m, int p, const float *xyz, float *te
     auto kern = fps_bucket_kernel<NW, BPW>;
     // per launch (a few hundred ns): the attribute is per device, and one process may drive several
     PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
-    kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx);
+    kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, nullptr);
     count_launch();
     PDM_CHECK_LAUNCH("farthest_point_sampling(bucket)");
     return PDM_OK;
 }
 
+// capacity (points) -> kernel with `nw` warps; returns PDM_ERR_UNSUPPORTED for combinations
+// that do not exist (BPW must stay within 1..32)
+template <int CAP>
+static int launch_cap(int nw, int b, int n, int m, int p, const float *xyz, float *temp, int *idx,
+                      cudaStream_t st) {
+    switch (nw) {
+#define PDM_NW(NWV)                                                                    \
+    case NWV:                                                                          \
+        if constexpr (CAP / (32 * NWV) >= 1 && CAP / (32 * NWV) <= 32)                 \
+            return launch_bucket<NWV, CAP / (32 * NWV)>(b, n, m, p, xyz, temp, idx, st); \
+        break;
+        PDM_NW(4) PDM_NW(8) PDM_NW(16) PDM_NW(32)
+#undef PDM_NW
+        default: break;
+    }
+    return fail(PDM_ERR_UNSUPPORTED, "farthest_point_sampling: no bucket kernel for cap %d with %d warps", CAP, nw);
+}
+
 }  // namespace pdm
+
+// Debug-only entry (not part of include/pdm_ops.h): per-phase cycle counters of the bucket
+// kernel, prof = device buffer of b*16*8 long long.  16384-point and 4096-point frames only.
+extern "C" int pdm_debug_fps_profile(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                     long long *prof, void *stream) {
+    using namespace pdm;
+    const int bs = ref_fps_block_size(n);
+    int p = 0;
+    while ((1 << p) < bs) ++p;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n > 4096 && n <= 16384) {
+        using L = FpsSmem<16, 32>;
+        auto kern = fps_bucket_kernel<16, 32, true>;
+        PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+        kern<<<b, 512, L::kBytes, st>>>(n, m, p, xyz, temp, idx, prof);
+    } else if (n <= 4096 && n > 2048) {
+        using L = FpsSmem<16, 8>;
+        auto kern = fps_bucket_kernel<16, 8, true>;
+        PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+        kern<<<b, 512, L::kBytes, st>>>(n, m, p, xyz, temp, idx, prof);
+    } else {
+        return fail(PDM_ERR_UNSUPPORTED, "debug_fps_profile: n=%d", n);
+    }
+    PDM_CHECK_LAUNCH("debug_fps_profile");
+    return PDM_OK;
+}
 
 extern "C" int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp,
                                            int *idx, void *stream) {
@@ -369,11 +525,16 @@ extern "C" int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz
     const char *force = getenv("PDM_FPS_KERNEL");  // "generic" | unset (debug/testing knob)
     const bool generic = force && force[0] == 'g';
     if (!generic && n >= 512 && n <= 16384) {
-        if (n <= 1024) return launch_bucket<32, 1>(b, n, m, p, xyz, temp, idx, st);
-        if (n <= 2048) return launch_bucket<32, 2>(b, n, m, p, xyz, temp, idx, st);
-        if (n <= 4096) return launch_bucket<32, 4>(b, n, m, p, xyz, temp, idx, st);
-        if (n <= 8192) return launch_bucket<32, 8>(b, n, m, p, xyz, temp, idx, st);
-        return launch_bucket<32, 16>(b, n, m, p, xyz, temp, idx, st);
+        // warps per CTA: few warps keep the per-round issue + barrier cost low, enough warps
+        // keep the (few) surviving bucket updates of a round in different warps.  Tuned on B200;
+        // PDM_FPS_NW overrides for experiments.
+        const char *nwenv = getenv("PDM_FPS_NW");
+        int nw = nwenv ? atoi(nwenv) : 0;
+        if (n <= 1024) return launch_cap<1024>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
+        if (n <= 2048) return launch_cap<2048>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
+        if (n <= 4096) return launch_cap<4096>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
+        if (n <= 8192) return launch_cap<8192>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
+        return launch_cap<16384>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
     }
     fps_generic_kernel<1024><<<b, 1024, 0, st>>>(n, m, p, xyz, temp, idx);
     count_launch();
