@@ -1,18 +1,33 @@
 // ball_query.cu -- fixed-radius neighbour query of the set-abstraction path.
 //
 // Semantics (ball_query_gpu.cu:15-51): for each centre scan the points in ascending
-// index k, keep the first `nsample` with d2 < radius^2 (d2 rounded as sqdist_ref,
-// radius^2 = rn(radius*radius) in fp32), pad the row with the first hit, and leave a
-// row with no hit untouched.
+// index k, keep the first `nsample` with d2 < radius^2 (d2 rounded as sqdist_ref with
+// dx = new_x - x, radius^2 = rn(radius*radius) in fp32), pad the row with the first hit, and
+// leave a row with no hit untouched.  Equivalently: the row holds the `nsample` SMALLEST
+// indices of the hit set in ascending order -- which does not depend on scan order.
 //
-// v0 kernel: one thread per centre like the reference, but the points stream through
-// shared memory in 12 KB tiles (one coalesced load per CTA instead of one broadcast
-// global load per thread and point) and a CTA stops as soon as all of its centres are
-// full.  Results are identical by construction: same scan order, same arithmetic.
+// Grid kernels (default)
+// ----------------------
+// The reference tests every centre against every point (M*N distance evaluations per frame).
+// Here the points of a frame are first binned into a uniform grid whose cells are at least
+// 1.01 * radius wide (bq_build_kernel: frame box, histogram, exclusive scan, scatter of
+// (x,y,z,k) records -- one CTA per frame).  A centre then only meets the 3x3x3 cells around
+// its own: fp32 rounding of the cell coordinate is ~1e-4 of a cell, far inside the 1% margin,
+// so no point with d2 < r^2 can lie outside that neighbourhood.  bq_query_kernel gives one
+// warp to each centre: the lanes stride over the candidate records (coalesced 16-byte loads),
+// evaluate the exact reference distance, and set bit k of a per-warp bitmap in shared memory
+// for every hit.  The bitmap is then read back in index order, which yields "first nsample
+// hits in ascending k" directly, whatever order the candidates were visited in.
+//
+// Tiled kernel (fallback, PDM_BQ_KERNEL=tiled): one thread per centre like the reference,
+// points streamed through shared memory; identical results by construction.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pdm {
 
+constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kBQTile = 1024;
 
 __global__ void __launch_bounds__(128)
@@ -52,6 +67,294 @@ ball_query_tiled_kernel(int n, int m, float radius2, int nsample,
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// grid build: one CTA per frame
+// ---------------------------------------------------------------------------------------
+struct BQGrid {        // per frame, written by the build kernel, read by the query kernel
+    float ox, oy, oz;  // origin (frame minimum over finite coordinates)
+    float ix, iy, iz;  // 1 / cell size per axis
+    int gx, gy, gz;    // cells per axis (z fastest in the linear index)
+    int ncell;
+};
+
+__device__ __forceinline__ int bq_cell_coord(float v, float o, float inv, int g) {
+    const float f = __fmul_rn(__fsub_rn(v, o), inv);
+    int c = (int)f;  // NaN -> 0, +-inf saturate
+    return max(0, min(g - 1, c));
+}
+
+constexpr int kBuildThreads = 1024;
+
+__global__ void __launch_bounds__(kBuildThreads)
+bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQGrid *__restrict__ grids,
+                int *__restrict__ cellid, int *__restrict__ cellend, float4 *__restrict__ sorted) {
+    __shared__ float red[6][kBuildThreads / 32];
+    __shared__ BQGrid sg;
+    __shared__ int wsum[kBuildThreads / 32];
+    __shared__ int carry, tile_total;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int bi = blockIdx.x;
+    const float *pts = xyz + (size_t)bi * n * 3;
+    int *cid = cellid + (size_t)bi * n;
+    int *cend = cellend + (size_t)bi * cmax;
+    float4 *srt = sorted + (size_t)bi * n;
+
+    // 1. frame box over finite coordinates
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int k = tid; k < n; k += kBuildThreads) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = __ldg(pts + (size_t)k * 3 + a);
+            if (fabsf(v) < INFINITY) {  // false for NaN and +-inf
+                lo[a] = fminf(lo[a], v);
+                hi[a] = fmaxf(hi[a], v);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(kFullMask, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(kFullMask, hi[a], o));
+        }
+        if (lane == 0) {
+            red[a][w] = lo[a];
+            red[3 + a][w] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float l[3], h[3];
+        for (int a = 0; a < 3; ++a) {
+            l[a] = INFINITY;
+            h[a] = -INFINITY;
+            for (int i = 0; i < kBuildThreads / 32; ++i) {
+                l[a] = fminf(l[a], red[a][i]);
+                h[a] = fmaxf(h[a], red[3 + a][i]);
+            }
+            if (!(l[a] <= h[a])) l[a] = h[a] = 0.f;  // no finite coordinate on this axis
+        }
+        // cells at least 1.01 r wide; fewer, wider cells when the frame would need > cmax of them
+        const float hmin = radius * 1.01f;
+        int g[3];
+        float ext[3];
+        for (int a = 0; a < 3; ++a) {
+            ext[a] = h[a] - l[a];
+            float cells = (hmin > 0.f && hmin < INFINITY) ? floorf(ext[a] / hmin) + 1.f : 1.f;
+            if (!(cells >= 1.f)) cells = 1.f;
+            g[a] = (int)fminf(cells, 1024.f);
+        }
+        while ((long long)g[0] * g[1] * g[2] > (long long)cmax) {
+            int a = g[0] >= g[1] ? (g[0] >= g[2] ? 0 : 2) : (g[1] >= g[2] ? 1 : 2);
+            g[a] = (g[a] + 1) / 2;
+        }
+        float inv[3];
+        for (int a = 0; a < 3; ++a) {
+            float cs = fmaxf(hmin, ext[a] / (float)g[a] * 1.0001f);
+            inv[a] = (cs > 0.f && cs < INFINITY) ? 1.0f / cs : 0.f;
+        }
+        sg.ox = l[0]; sg.oy = l[1]; sg.oz = l[2];
+        sg.ix = inv[0]; sg.iy = inv[1]; sg.iz = inv[2];
+        sg.gx = g[0]; sg.gy = g[1]; sg.gz = g[2];
+        sg.ncell = g[0] * g[1] * g[2];
+        grids[bi] = sg;
+        carry = 0;
+    }
+    __syncthreads();
+    const BQGrid G = sg;
+
+    // 2. histogram (global atomics; the counters live in cellend)
+    for (int c = tid; c < G.ncell; c += kBuildThreads) cend[c] = 0;
+    __syncthreads();
+    for (int k = tid; k < n; k += kBuildThreads) {
+        const int cx = bq_cell_coord(__ldg(pts + (size_t)k * 3 + 0), G.ox, G.ix, G.gx);
+        const int cy = bq_cell_coord(__ldg(pts + (size_t)k * 3 + 1), G.oy, G.iy, G.gy);
+        const int cz = bq_cell_coord(__ldg(pts + (size_t)k * 3 + 2), G.oz, G.iz, G.gz);
+        const int c = (cx * G.gy + cy) * G.gz + cz;
+        cid[k] = c;
+        atomicAdd(&cend[c], 1);
+    }
+    __syncthreads();
+
+    // 3. exclusive scan of the counts, in place (tiles of 4 * kBuildThreads cells)
+    for (int base = 0; base < G.ncell; base += 4 * kBuildThreads) {
+        const int c0 = base + tid * 4;
+        int v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = (c0 + q < G.ncell) ? cend[c0 + q] : 0;
+        const int tsum = v[0] + v[1] + v[2] + v[3];
+        int incl = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) wsum[w] = incl;
+        __syncthreads();
+        if (w == 0) {
+            int s = wsum[lane];
+            int si = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(kFullMask, si, o);
+                if (lane >= o) si += y;
+            }
+            wsum[lane] = si - s;  // exclusive warp offsets
+            if (lane == 31) tile_total = si;
+        }
+        __syncthreads();
+        int run = carry + wsum[w] + incl - tsum;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (c0 + q < G.ncell) cend[c0 + q] = run;
+            run += v[q];
+        }
+        __syncthreads();
+        if (tid == 0) carry += tile_total;
+        __syncthreads();
+    }
+
+    // 4. scatter: the start cursors advance to the (exclusive) ends
+    for (int k = tid; k < n; k += kBuildThreads) {
+        const int slot = atomicAdd(&cend[cid[k]], 1);
+        srt[slot] = make_float4(__ldg(pts + (size_t)k * 3 + 0), __ldg(pts + (size_t)k * 3 + 1),
+                                __ldg(pts + (size_t)k * 3 + 2), __int_as_float(k));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// grid query: one warp per centre
+// ---------------------------------------------------------------------------------------
+constexpr int kQueryWarps = 8;
+
+__global__ void __launch_bounds__(kQueryWarps * 32)
+bq_query_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2 /*bitmap words per lane = 1 << wpl_log2*/,
+                const float *__restrict__ new_xyz, const BQGrid *__restrict__ grids,
+                const int *__restrict__ cellend, const float4 *__restrict__ sorted,
+                int *__restrict__ idx) {
+    extern __shared__ unsigned bitmap_all[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int bi = blockIdx.y;
+    const int qi = blockIdx.x * kQueryWarps + w;
+    if (qi >= m) return;  // whole warp
+    const int wpl = 1 << wpl_log2;
+    const int stride = wpl | 1;  // odd stride: lane-contiguous ownership without bank conflicts
+    unsigned *bm = bitmap_all + (size_t)w * 32 * stride;
+    unsigned *mine = bm + lane * stride;  // words [lane*wpl, lane*wpl + wpl) of the frame's bitmap
+    for (int j = 0; j < wpl; ++j) mine[j] = 0u;
+
+    const BQGrid G = grids[bi];
+    const float *q = new_xyz + ((size_t)bi * m + qi) * 3;
+    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    const int cx = bq_cell_coord(qx, G.ox, G.ix, G.gx);
+    const int cy = bq_cell_coord(qy, G.oy, G.iy, G.gy);
+    const int cz = bq_cell_coord(qz, G.oz, G.iz, G.gz);
+    const int *cend = cellend + (size_t)bi * cmax;
+    const float4 *srt = sorted + (size_t)bi * n;
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, G.gz - 1);
+    __syncwarp();
+
+    // lanes 0..8 fetch the candidate range of their (dx,dy) column, then the warp walks them
+    int rs = 0, re = 0;
+    if (lane < 9) {
+        const int x = cx + lane / 3 - 1, y = cy + lane % 3 - 1;
+        if (x >= 0 && x < G.gx && y >= 0 && y < G.gy) {
+            const int c0 = (x * G.gy + y) * G.gz + z0;
+            const int c1 = (x * G.gy + y) * G.gz + z1;
+            rs = c0 == 0 ? 0 : __ldg(cend + c0 - 1);
+            re = __ldg(cend + c1);
+        }
+    }
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int s = __shfl_sync(kFullMask, rs, r), e = __shfl_sync(kFullMask, re, r);
+        for (int i = s + lane; i < e; i += 32) {
+            const float4 pt = __ldg(srt + i);
+            const float d2 = sqdist_ref(__fsub_rn(qx, pt.x), __fsub_rn(qy, pt.y), __fsub_rn(qz, pt.z));
+            if (d2 < radius2) {
+                const unsigned k = (unsigned)__float_as_int(pt.w);
+                const unsigned word = k >> 5;
+                atomicOr(&bm[(word >> wpl_log2) * stride + (word & (wpl - 1))], 1u << (k & 31u));
+            }
+        }
+    }
+    __syncwarp();
+
+    // hits in ascending index order = bitmap order; lane owns a contiguous slice of it
+    int cnt = 0;
+    for (int j = 0; j < wpl; ++j) cnt += __popc(mine[j]);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(kFullMask, incl, 31);
+    if (total == 0) return;  // no hit: the row stays as the caller left it
+    int *row = idx + ((size_t)bi * m + qi) * nsample;
+    int pos = incl - cnt;
+    int first = 0x7fffffff;
+    if (cnt > 0 && (pos < nsample || pos == 0)) {
+        for (int j = 0; j < wpl && pos < nsample; ++j) {
+            unsigned bits = mine[j];
+            while (bits && pos < nsample) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const int k = ((lane * wpl + j) << 5) + b;
+                if (first == 0x7fffffff) first = k;
+                row[pos++] = k;
+            }
+        }
+    }
+    if (total < nsample) {  // pad with the first (smallest) hit
+        const int f = __reduce_min_sync(kFullMask, first);
+        for (int l = total + lane; l < nsample; l += 32) row[l] = f;
+    }
+}
+
+static int ball_query_grid(int b, int n, int m, float radius, float radius2, int nsample,
+                           const float *new_xyz, const float *xyz, int *idx, cudaStream_t st) {
+    // cells per frame: ~4 per point, power of two, bounded
+    int cmax = 4096;
+    while (cmax < 4 * n && cmax < 262144) cmax <<= 1;
+    const int words = (n + 31) / 32;
+    int wpl_log2 = 0;  // bitmap words per lane, rounded up to a power of two
+    while ((32 << wpl_log2) < words) ++wpl_log2;
+    const int wpl = 1 << wpl_log2;
+    const size_t smem = (size_t)kQueryWarps * 32 * (wpl | 1) * sizeof(unsigned);
+    if (smem > 200 * 1024) return PDM_ERR_UNSUPPORTED;  // caller falls back to the tiled kernel
+
+    const size_t sz_grid = ((sizeof(BQGrid) * b + 255) / 256) * 256;
+    const size_t sz_cid = (((size_t)b * n * sizeof(int) + 255) / 256) * 256;
+    const size_t sz_cend = (size_t)b * cmax * sizeof(int);
+    const size_t sz_sorted = (size_t)b * n * sizeof(float4);
+    char *scratch = nullptr;
+    PDM_CHECK_CUDA(cudaMallocAsync((void **)&scratch, sz_grid + sz_cid + sz_cend + sz_sorted, st));
+    BQGrid *grids = reinterpret_cast<BQGrid *>(scratch);
+    int *cid = reinterpret_cast<int *>(scratch + sz_grid);
+    int *cend = reinterpret_cast<int *>(scratch + sz_grid + sz_cid);
+    float4 *sorted = reinterpret_cast<float4 *>(scratch + sz_grid + sz_cid + sz_cend);
+
+    bq_build_kernel<<<b, kBuildThreads, 0, st>>>(n, radius, cmax, xyz, grids, cid, cend, sorted);
+    count_launch();
+    cudaError_t e1 = cudaGetLastError();
+    if (e1 == cudaSuccess) {
+        if (smem > 48 * 1024)
+            e1 = cudaFuncSetAttribute(bq_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e1 == cudaSuccess) {
+            dim3 grid((m + kQueryWarps - 1) / kQueryWarps, b);
+            bq_query_kernel<<<grid, kQueryWarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
+                                                                 grids, cend, sorted, idx);
+            count_launch();
+            e1 = cudaGetLastError();
+        }
+    }
+    cudaFreeAsync(scratch, st);
+    if (e1 != cudaSuccess) return fail((int)e1, "ball_query(grid): %s", cudaGetErrorString(e1));
+    return PDM_OK;
+}
+
 }  // namespace pdm
 
 extern "C" int pdm_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
@@ -62,8 +365,17 @@ extern "C" int pdm_ball_query(int b, int n, int m, float radius, int nsample, co
     if (!new_xyz || !xyz || !idx) return fail(PDM_ERR_INVALID_ARG, "ball_query: null pointer");
     if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "ball_query: batch %d > 65535", b);
     const float radius2 = radius * radius;  // fp32, as ball_query_gpu.cu:29
+    cudaStream_t st = (cudaStream_t)stream;
+    const char *force = getenv("PDM_BQ_KERNEL");  // "tiled" | unset (debug/testing knob)
+    const bool tiled = force && force[0] == 't';
+    // the grid needs a usable radius; NaN / non-positive radii have no hits at all or are
+    // handled by the scan kernel with the reference's exact comparison
+    if (!tiled && radius > 0.f && radius < INFINITY) {
+        const int rc = ball_query_grid(b, n, m, radius, radius2, nsample, new_xyz, xyz, idx, st);
+        if (rc != PDM_ERR_UNSUPPORTED) return rc;
+    }
     dim3 grid((m + 127) / 128, b);
-    ball_query_tiled_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
+    ball_query_tiled_kernel<<<grid, 128, 0, st>>>(n, m, radius2, nsample, new_xyz, xyz, idx);
     count_launch();
     PDM_CHECK_LAUNCH("ball_query");
     return PDM_OK;
