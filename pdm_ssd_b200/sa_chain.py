@@ -1,0 +1,115 @@
+"""The set-abstraction operator chain of BASELINE config 2, as one callable.
+
+    SA1: FPS 16384 -> 4096, gather centres, ball query r=0.8 / 32, group xyz, group features (C=1)
+    SA2: FPS  4096 -> 1024, gather centres, ball query r=1.6 / 32, group xyz, group features (C=64)
+
+It issues exactly the operator calls `_PointnetSAModuleBase.forward` + `QueryAndGroup.forward`
+make in the reference (pointnet2_modules.py:19-55, pointnet2_utils.py:241-264) -- through the
+nine-function backend API, so the same object drives our kernels or the reference extension --
+with all outputs pre-allocated (steady-state serving: no allocator traffic inside a step).
+"""
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import pointnet2_batch_cuda as _ours
+
+
+@dataclass
+class SALayerCfg:
+    npoint: int
+    radius: float
+    nsample: int
+    channels: int  # feature channels grouped at this layer
+
+
+KITTI_CHAIN = (SALayerCfg(4096, 0.8, 32, 1), SALayerCfg(1024, 1.6, 32, 64))
+
+
+def algorithmic_bytes_per_frame(n_points: int, layers=KITTI_CHAIN) -> Dict[str, int]:
+    """Compulsory HBM bytes per frame, op by op (SURVEY.md section 8d / BASELINE.md 2.4):
+    every API-visible input read once, every API-visible output written once, fp32/int32."""
+    out = {}
+    n = n_points
+    for li, L in enumerate(layers, 1):
+        m, s, c = L.npoint, L.nsample, L.channels
+        out["sa%d_fps" % li] = 12 * n + 4 * m
+        out["sa%d_gather" % li] = 4 * m + 24 * m
+        out["sa%d_ball_query" % li] = 12 * n + 12 * m + 4 * m * s
+        out["sa%d_group_xyz" % li] = 4 * m * s + 12 * n + 12 * m * s
+        out["sa%d_group_feat" % li] = 4 * m * s + 4 * c * n + 4 * c * m * s
+        n = m
+    out["total"] = sum(out.values())
+    return out
+
+
+class SAChain:
+    def __init__(self, batch: int, n_points: int = 16384, layers=KITTI_CHAIN, device="cuda:0", backend=None):
+        self.B, self.N, self.layers = batch, n_points, tuple(layers)
+        self.dev = torch.device(device)
+        self.be = backend if backend is not None else _ours
+        self.ws = []
+        n = n_points
+        for L in self.layers:
+            m, s, c = L.npoint, L.nsample, L.channels
+            f32 = dict(dtype=torch.float32, device=self.dev)
+            i32 = dict(dtype=torch.int32, device=self.dev)
+            self.ws.append(dict(
+                temp=torch.empty((batch, n), **f32), fps_idx=torch.empty((batch, m), **i32),
+                xyz_t=torch.empty((batch, 3, n), **f32), new_t=torch.empty((batch, 3, m), **f32),
+                new_xyz=torch.empty((batch, m, 3), **f32), ball_idx=torch.empty((batch, m, s), **i32),
+                grouped_xyz=torch.empty((batch, 3, m, s), **f32), grouped_feat=torch.empty((batch, c, m, s), **f32)))
+            n = m
+
+    def run(self, xyz: torch.Tensor, feats) -> Dict[str, torch.Tensor]:
+        """xyz (B,N,3) device tensor; feats[i] (B,C_i,N_i) device tensor per layer.
+        Returns the per-layer workspaces (device tensors, overwritten by the next call)."""
+        be, B = self.be, self.B
+        cur, n = xyz, self.N
+        for L, ws, feat in zip(self.layers, self.ws, feats):
+            m, s, c = L.npoint, L.nsample, L.channels
+            ws["temp"].fill_(1e10)                                      # pointnet2_utils.py:26
+            be.farthest_point_sampling_wrapper(B, n, m, cur, ws["temp"], ws["fps_idx"])
+            ws["xyz_t"].copy_(cur.transpose(1, 2))                      # pointnet2_modules.py:30
+            be.gather_points_wrapper(B, 3, n, m, ws["xyz_t"], ws["fps_idx"], ws["new_t"])
+            ws["new_xyz"].copy_(ws["new_t"].transpose(1, 2))            # pointnet2_modules.py:32-35
+            ws["ball_idx"].zero_()                                      # pointnet2_utils.py:218
+            be.ball_query_wrapper(B, n, m, L.radius, s, ws["new_xyz"], cur, ws["ball_idx"])
+            be.group_points_wrapper(B, 3, n, m, s, ws["xyz_t"], ws["ball_idx"], ws["grouped_xyz"])
+            ws["grouped_xyz"].sub_(ws["new_t"].unsqueeze(-1))           # pointnet2_utils.py:252
+            be.group_points_wrapper(B, c, n, m, s, feat, ws["ball_idx"], ws["grouped_feat"])
+            cur, n = ws["new_xyz"], m
+        return self.ws
+
+
+class HostSAChain:
+    """End-to-end form: host (pinned) buffers in, host results out; copies inside the call.
+
+    Inputs per step: points (B,N,4) [x,y,z,intensity] and the SA2 feature tensor (B,64,4096).
+    Result per step: per layer the sampled indices, centres and ball-query indices."""
+
+    def __init__(self, batch, n_points=16384, layers=KITTI_CHAIN, device="cuda:0", backend=None):
+        self.chain = SAChain(batch, n_points, layers, device, backend)
+        dev = self.chain.dev
+        self.d_points = torch.empty((batch, n_points, 4), dtype=torch.float32, device=dev)
+        self.d_xyz = torch.empty((batch, n_points, 3), dtype=torch.float32, device=dev)
+        self.d_feat1 = torch.empty((batch, 1, n_points), dtype=torch.float32, device=dev)
+        self.d_feat2 = torch.empty((batch, layers[1].channels, layers[0].npoint), dtype=torch.float32, device=dev)
+        self.h_out = []
+        for ws in self.chain.ws:
+            self.h_out.append({k: torch.empty(ws[k].shape, dtype=ws[k].dtype).pin_memory()
+                               for k in ("fps_idx", "new_xyz", "ball_idx")})
+        self.h2d_bytes = self.d_points.numel() * 4 + self.d_feat2.numel() * 4
+        self.d2h_bytes = sum(t.numel() * t.element_size() for o in self.h_out for t in o.values())
+
+    def run(self, h_points: torch.Tensor, h_feat2: torch.Tensor):
+        self.d_points.copy_(h_points, non_blocking=True)
+        self.d_feat2.copy_(h_feat2, non_blocking=True)
+        self.d_xyz.copy_(self.d_points[..., :3])
+        self.d_feat1.copy_(self.d_points[..., 3:].transpose(1, 2))
+        ws = self.chain.run(self.d_xyz, (self.d_feat1, self.d_feat2))
+        for o, w in zip(self.h_out, ws):
+            for k, t in o.items():
+                t.copy_(w[k], non_blocking=True)
+        return self.h_out
