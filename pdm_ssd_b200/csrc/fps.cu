@@ -27,6 +27,8 @@
 //   O(buckets/warp) bound checks + a couple of 32-point updates + one block-wide argmax
 //   instead of a sweep over all n points.  Running minima live in registers, coordinates in
 //   shared memory (SoA, conflict-free), the argmax uses redux.sync and one barrier/round.
+//   SEVERAL samples are accepted per barrier round when that is provably what the sequential
+//   algorithm would do (see "multi-sample rounds" below).
 // fps_generic_kernel: any n; same key trick, temp in global memory.
 #include <stdlib.h>
 
@@ -115,14 +117,17 @@ __device__ __forceinline__ float ord2f(unsigned u) {
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-template <int NW, int BPW>
+template <int NW, int BPW, int KMAX>
 struct FpsSmem {
     static constexpr int CAP = NW * BPW * 32;
-    // [0, 12*CAP): sx, sy, sz (aliased by the 8*CAP-byte sort keys during set-up)
-    // then pub[2][NW] uint2 (value bits, position), pubtk[2][NW] tiekeys, frame-box scratch
+    // [0, 12*CAP): sx, sy, sz (aliased by the 8*CAP-byte sort keys during set-up), then
+    // pub[2][2*NW] uint2 (value bits, position) -- two candidates per warp,
+    // pubU[2][NW] bound on every other point of the warp, samp[NW][KMAX] float4 accepted samples
+    // (one private copy per warp), frame-box scratch.
     static constexpr size_t kPubOff = (size_t)12 * CAP;
-    static constexpr size_t kTkOff = kPubOff + sizeof(uint2) * 2 * NW;
-    static constexpr size_t kBoxOff = kTkOff + sizeof(unsigned) * 2 * NW;
+    static constexpr size_t kUOff = kPubOff + sizeof(uint2) * 2 * 2 * NW;
+    static constexpr size_t kSampOff = ((kUOff + sizeof(unsigned) * 2 * NW + 15) / 16) * 16;
+    static constexpr size_t kBoxOff = kSampOff + sizeof(float4) * NW * KMAX;
     static constexpr size_t kBytes = kBoxOff + sizeof(float) * 6 * NW;
 };
 
@@ -186,22 +191,40 @@ __device__ __forceinline__ void reg_store(float (&t)[BPW], int jj, float v) {
     }
 }
 
-// PROF: debug build that accumulates clock64() per phase and per warp into `prof`
-// ([frame][warp][8] = A, B, C, barrier wait, D cycles, #bucket updates, #C runs, total).
-template <int NW, int BPW, bool PROF = false>
+// Multi-sample rounds
+// -------------------
+// A barrier round costs ~1100 cycles of dependent latency, so the kernel tries to emit several
+// samples per round.  Every warp publishes TWO candidates -- the best point of its best and of
+// its second-best bucket, with exact values -- and a bound U_w on all its other points (the
+// maxima of its remaining buckets and the runner-up inside the two candidate buckets).  With
+// U = max_w U_w, every warp then replays the sequential algorithm on the 2*NW candidates alone
+// (one per lane, redundantly, no further barrier):
+//   pick 1: the exact block argmax with the reference's tie-break, exactly as a 1-sample round;
+//   pick i>1: update the candidates' minima with the previous pick (same sqdist_ref rounding);
+//             if the largest candidate value is unique and STRICTLY greater than U it is the
+//             unique global maximum -- every non-candidate is <= U because minima only decrease --
+//             so it is what the reference picks next, no tie-break needed; otherwise stop.
+// The accepted samples (<= KMAX) are then applied to the buckets together.  On KITTI-shaped
+// frames this emits ~6 samples per barrier.
+// TRACE: debug instantiation; frame 0 dumps clock64() stamps per round and warp into `trace`
+// ([round][warp][8] = t_start, t_afterA, t_afterB, t_afterC(before barrier), t_afterBarrier,
+//  t_afterPick1, t_afterLoop, K | nupdates<<8).
+template <int NW, int BPW, int KMAX, bool TRACE = false>
 __global__ void __launch_bounds__(NW * 32, 1)
 fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__restrict__ temp,
-                  int *__restrict__ idxs, long long *__restrict__ prof = nullptr) {
-    using L = FpsSmem<NW, BPW>;
+                  int *__restrict__ idxs, int *__restrict__ stats, long long *__restrict__ trace = nullptr) {
+    using L = FpsSmem<NW, BPW, KMAX>;
     constexpr int CAP = L::CAP;
     constexpr int T = NW * 32;
-    static_assert(BPW <= 32 && NW <= 32, "one lane per owned bucket / per warp");
+    static_assert(BPW <= 32 && NW <= 16, "one lane per owned bucket; two candidates per warp in one warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sx = reinterpret_cast<float *>(smem_raw);
     float *sy = sx + CAP;
     float *sz = sy + CAP;
     unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
     uint2 *pub = reinterpret_cast<uint2 *>(smem_raw + L::kPubOff);
+    unsigned *pubU = reinterpret_cast<unsigned *>(smem_raw + L::kUOff);
+    float4 *samp = reinterpret_cast<float4 *>(smem_raw + L::kSampOff);
     float *box = reinterpret_cast<float *>(smem_raw + L::kBoxOff);
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -300,7 +323,7 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
     // per-bucket state, held by lane j of the owning warp
     float blox = INFINITY, bloy = INFINITY, bloz = INFINITY;
     float bhix = -INFINITY, bhiy = -INFINITY, bhiz = -INFINITY;
-    unsigned bmax = 0u, bwl = 0u;
+    unsigned bmax = 0u, bwl = 0u, bsec = 0u;  // max (bits), lane holding it, runner-up (bits)
 #pragma unroll
     for (int j = 0; j < BPW; ++j) {
         const int pos = ((j * NW + w) << 5) + lane;
@@ -329,185 +352,275 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
         const unsigned cand = (tb == mx && !pad) ? fps_tiekey(kk_[j], p, bsmask) : kPadKey;
         const unsigned tkm = __reduce_min_sync(kFull, cand);
         const unsigned wl = __ffs(__ballot_sync(kFull, cand == tkm)) - 1;
+        const unsigned sec = __reduce_max_sync(kFull, lane == (int)wl ? 0u : tb);
         if (lane == j) {
             blox = ord2f(lx); bloy = ord2f(ly); bloz = ord2f(lz);
             bhix = ord2f(hx); bhiy = ord2f(hy); bhiz = ord2f(hz);
-            bmax = mx; bwl = wl;
+            bmax = mx; bwl = wl; bsec = sec;
         }
     }
+    if (lane == 0) samp[w * KMAX] = make_float4(__ldg(dataset + 0), __ldg(dataset + 1), __ldg(dataset + 2), 0.f);
     __syncthreads();
 
     // ---- 4. rounds -------------------------------------------------------------------------
-    float cx = __ldg(dataset + 0), cy = __ldg(dataset + 1), cz = __ldg(dataset + 2);  // sample 0 = point 0
-    unsigned wm = 0u, wpos = 0u;  // cached best of this warp (value bits, sorted position)
-    bool dirty = true;
     const int wbase = (w << 5) + lane;                               // my slot in owned bucket 0
     const unsigned bbase = (unsigned)(lane * (NW * 32) + (w << 5));  // first slot of owned bucket `lane`
     // tiekey of the point at sorted position pos (global read: slow paths only)
     auto tiekey_at = [&](unsigned pos) -> unsigned {
         return pos < (unsigned)n ? fps_tiekey(pmap[pos], p, bsmask) : kPadKey;
     };
-    unsigned pending = 0u;  // thread 0: original index of the previous round's winner (in flight)
-    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    long long tq = 0, tq0 = 0;
-    if (PROF) tq0 = tq = clock64();
-#define PDM_TICK(SLOT)                         \
-    if (PROF) {                                \
-        const long long now = clock64();       \
-        pc[SLOT] += now - tq;                  \
-        tq = now;                              \
-    }
-    for (int j = 1; j < m; ++j) {
-        // A. which of my buckets can change?  exact lower bound of d over the bucket box
-        // (lanes >= BPW hold an empty box: gap = +inf, never active -- no divergent branch needed)
-        const float gx = fmaxf(fmaxf(__fsub_rn(blox, cx), __fsub_rn(cx, bhix)), 0.f);
-        const float gy = fmaxf(fmaxf(__fsub_rn(bloy, cy), __fsub_rn(cy, bhiy)), 0.f);
-        const float gz = fmaxf(fmaxf(__fsub_rn(bloz, cz), __fsub_rn(cz, bhiz)), 0.f);
-        unsigned mask = __ballot_sync(kFull, sqdist_ref(gx, gy, gz) < __uint_as_float(bmax));
-        PDM_TICK(0)
-        // B. update the surviving buckets, one 32-point bucket per iteration
+    unsigned c1v = 0u, c1p = 0u, c2v = 0u, c2p = 0u, wU = 0u;  // cached candidates / bound of this warp
+    bool dirty = true;
+    int K = 1;         // samples accepted in the previous round, waiting to be applied (sample 0 first)
+    int j = 1;         // samples emitted so far
+    int rounds = 0;
+    int pend_slot = -1;       // warp 0: output slot of the sample this lane's candidate became ...
+    unsigned pend_val = 0u;   // ... and its original index (global load in flight since last round)
+    long long tr[8];
+    int nupd = 0;
+#define PDM_STAMP(I) if (TRACE) tr[I] = clock64();
+    for (;;) {
+        PDM_STAMP(0)
+        nupd = 0;
+        // A. which of my buckets can change?  exact lower bound of d over the bucket box, for
+        //    each of the K new samples (lanes >= BPW hold an empty box: gap = +inf, never active).
+        //    Runtime loop over the K samples (warp-private copy in shared memory, broadcast reads):
+        //    this phase is issue-bound -- every warp runs it for every sample.
+        const float4 *ws = samp + w * KMAX;
+        unsigned amask = 0u;  // bit k: sample k can change my bucket
+        {
+            const float bm = __uint_as_float(bmax);
+            // two samples per iteration: the two bound chains are independent and overlap
+            // (entries beyond K are stale but finite or zero; their bits are masked off)
+            for (int k = 0; k < K; k += 2) {
+                const float4 c = ws[k], e2 = ws[(k + 1 < KMAX) ? k + 1 : k];
+                const float gx = fmaxf(fmaxf(__fsub_rn(blox, c.x), __fsub_rn(c.x, bhix)), 0.f);
+                const float gy = fmaxf(fmaxf(__fsub_rn(bloy, c.y), __fsub_rn(c.y, bhiy)), 0.f);
+                const float gz = fmaxf(fmaxf(__fsub_rn(bloz, c.z), __fsub_rn(c.z, bhiz)), 0.f);
+                const float hx = fmaxf(fmaxf(__fsub_rn(blox, e2.x), __fsub_rn(e2.x, bhix)), 0.f);
+                const float hy = fmaxf(fmaxf(__fsub_rn(bloy, e2.y), __fsub_rn(e2.y, bhiy)), 0.f);
+                const float hz = fmaxf(fmaxf(__fsub_rn(bloz, e2.z), __fsub_rn(e2.z, bhiz)), 0.f);
+                const unsigned a0 = sqdist_ref(gx, gy, gz) < bm ? 1u : 0u;
+                const unsigned a1 = (k + 1 < K && sqdist_ref(hx, hy, hz) < bm) ? 2u : 0u;
+                amask |= (a0 | a1) << k;
+            }
+        }
+        unsigned mask = __ballot_sync(kFull, amask != 0u);
+        PDM_STAMP(1)
+        // B. update the surviving buckets (32 points = 32 lanes each) with the samples that
+        //    reach them (usually one)
         while (mask) {
             const int jj = 31 - __clz(mask);
             mask ^= 1u << jj;
+            unsigned smask = __shfl_sync(kFull, amask, jj);
             const int pos = jj * (NW * 32) + wbase;
-            const float d = sqdist_ref(__fsub_rn(sx[pos], cx), __fsub_rn(sy[pos], cy), __fsub_rn(sz[pos], cz));
-            const float nt = fminf(d, reg_select<BPW>(t, jj));
+            const float x = sx[pos], y = sy[pos], z = sz[pos];
+            float nt = reg_select<BPW>(t, jj);
+            while (smask) {
+                const int k = 31 - __clz(smask);
+                smask ^= 1u << k;
+                const float4 c = ws[k];
+                nt = fminf(sqdist_ref(__fsub_rn(x, c.x), __fsub_rn(y, c.y), __fsub_rn(z, c.z)), nt);
+            }
             const unsigned tb = __float_as_uint(nt);
             const unsigned mx = __reduce_max_sync(kFull, tb);
             const bool hit = tb == mx;
             unsigned wl = __reduce_max_sync(kFull, hit ? (unsigned)lane : 0u);
-            if (multi_bit(__ballot_sync(kFull, hit))) {  // duplicates: smallest tiekey wins
+            unsigned sec = __reduce_max_sync(kFull, hit ? 0u : tb);  // next distinct value ...
+            if (multi_bit(__ballot_sync(kFull, hit))) {  // duplicates: smallest tiekey wins,
                 const unsigned cand = hit ? tiekey_at(pos) : kPadKey;
                 const unsigned tkm = __reduce_min_sync(kFull, cand);
                 wl = __reduce_max_sync(kFull, cand == tkm ? (unsigned)lane : 0u);
+                sec = mx;                                // ... and the runner-up equals the maximum
             }
-            if (lane == jj) { bmax = mx; bwl = wl; }
+            if (lane == jj) { bmax = mx; bwl = wl; bsec = sec; }
             reg_store<BPW>(t, jj, nt);
             dirty = true;
-            if (PROF) pc[5] += 1;
+            ++nupd;
         }
-        PDM_TICK(1)
-        // C. best of this warp (only when one of its buckets changed)
+        if (j >= m) break;
+        ++rounds;
+        PDM_STAMP(2)
+        // C. this warp's two candidates and the bound on everything else it owns
         if (dirty) {
             dirty = false;
             const unsigned v = lane < BPW ? bmax : 0u;
-            wm = __reduce_max_sync(kFull, v);
-            const bool hit = lane < BPW && v == wm;
-            wpos = __reduce_max_sync(kFull, hit ? bbase + bwl : 0u);
-            if (multi_bit(__ballot_sync(kFull, hit))) {  // several buckets share the maximum
-                const unsigned c2 = hit ? tiekey_at(bbase + bwl) : kPadKey;
-                const unsigned tkm = __reduce_min_sync(kFull, c2);
-                wpos = __reduce_max_sync(kFull, (hit && c2 == tkm) ? bbase + bwl : 0u);
+            c1v = __reduce_max_sync(kFull, v);
+            const bool hit1 = lane < BPW && v == c1v;
+            unsigned src1 = __reduce_max_sync(kFull, hit1 ? (unsigned)lane : 0u);
+            c2v = __reduce_max_sync(kFull, hit1 ? 0u : v);  // next distinct value (issued early)
+            if (multi_bit(__ballot_sync(kFull, hit1))) {    // several buckets share the maximum
+                const unsigned cc = hit1 ? tiekey_at(bbase + bwl) : kPadKey;
+                const unsigned tkm = __reduce_min_sync(kFull, cc);
+                src1 = __reduce_max_sync(kFull, (hit1 && cc == tkm) ? (unsigned)lane : 0u);
+                c2v = c1v;  // an equal-valued bucket becomes the second candidate
             }
-            if (PROF) pc[6] += 1;
+            const bool hit2 = lane < BPW && lane != (int)src1 && v == c2v;
+            const unsigned src2 = __reduce_max_sync(kFull, hit2 ? (unsigned)lane : 0u);
+            const bool has2 = __ballot_sync(kFull, hit2) != 0u;
+            const bool mine = lane == (int)src1 || (has2 && lane == (int)src2);
+            wU = __reduce_max_sync(kFull, mine ? bsec : v);
+            c1p = __shfl_sync(kFull, bbase + bwl, src1);
+            c2p = __shfl_sync(kFull, bbase + bwl, src2);
+            if (!has2) { c2v = 0u; c2p = c1p; }  // single-bucket warp: a dead second candidate
         }
-        PDM_TICK(2)
-        const int par = (j & 1) * NW;
-        if (lane == 0) pub[par + w] = make_uint2(wm, wpos);
+        const int par = (rounds & 1);
+        if (lane == 0) {
+            pub[par * 2 * NW + 2 * w] = make_uint2(c1v, c1p);
+            pub[par * 2 * NW + 2 * w + 1] = make_uint2(c2v, c2p);
+            pubU[par * NW + w] = wU;
+        }
+        PDM_STAMP(3)
         __syncthreads();
-        PDM_TICK(3)
-        // D. block argmax (every warp redundantly: no second barrier)
-        uint2 e = make_uint2(0u, 0u);
-        if (lane < NW) e = pub[par + lane];
-        const unsigned gm = __reduce_max_sync(kFull, e.x);
-        const bool ghit = lane < NW && e.x == gm;
-        unsigned gpos = __reduce_max_sync(kFull, ghit ? e.y : 0u);
-        if (multi_bit(__ballot_sync(kFull, ghit))) {  // several warps share the maximum
+        // D. every warp replays the sequential selection on the 2*NW candidates (one per lane)
+        if (w == 0 && pend_slot >= 0) out[pend_slot] = (int)pend_val;
+        pend_slot = -1;
+        const bool live = lane < 2 * NW;
+        const uint2 e = live ? pub[par * 2 * NW + lane] : make_uint2(0u, 0u);
+        if (TRACE) { tr[4] = clock64() + (long long)(e.x & 0u); }
+        const unsigned U = __reduce_max_sync(kFull, lane < NW ? pubU[par * NW + lane] : 0u);
+        const float x = sx[e.y], y = sy[e.y], z = sz[e.y];
+        float v = __uint_as_float(e.x);
+        // pick 1: exact argmax over the warps' first candidates, reference tie-break
+        const bool first = live && !(lane & 1);
+        const unsigned gm = __reduce_max_sync(kFull, first ? e.x : 0u);
+        bool ghit = first && e.x == gm;
+        if (multi_bit(__ballot_sync(kFull, ghit))) {
             const unsigned c3 = ghit ? tiekey_at(e.y) : kPadKey;
             const unsigned gtk = __reduce_min_sync(kFull, c3);
-            gpos = __reduce_max_sync(kFull, (ghit && c3 == gtk) ? e.y : 0u);
+            ghit = ghit && c3 == gtk;
         }
-        cx = sx[gpos];
-        cy = sy[gpos];
-        cz = sz[gpos];
-        // output index: software-pipelined so the global read of the map never stalls a round
-        if (tid == 0) {
-            if (j > 1) out[j - 1] = (int)pending;
-            pending = pmap[gpos];
+        if (TRACE) { v += 0.f * (float)(gm & 1u) + 0.f * x; }  // keep pick 1 inside its window
+        PDM_STAMP(5)
+        const int kmax_now = min(KMAX, m - j);
+        K = 0;
+        for (;;) {
+            if (ghit) {
+                samp[w * KMAX + K] = make_float4(x, y, z, 0.f);
+                pend_slot = j + K;  // (only warp 0 reports; see below)
+            }
+            ++K;
+            if (K >= kmax_now) break;
+            __syncwarp();
+            const float4 s4 = samp[w * KMAX + K - 1];
+            v = fminf(sqdist_ref(__fsub_rn(x, s4.x), __fsub_rn(y, s4.y), __fsub_rn(z, s4.z)), v);
+            const unsigned vb = live ? __float_as_uint(v) : 0u;
+            const unsigned g2 = __reduce_max_sync(kFull, vb);
+            if (!(g2 > U)) break;              // a non-candidate may be as large: stop
+            ghit = live && vb == g2;
+            if (multi_bit(__ballot_sync(kFull, ghit))) break;  // equal candidates: let pick 1 of the next round decide
         }
-        if (PROF) { cx += 0.f * __uint_as_float(gpos); }  // keep the loads inside the D window
-        PDM_TICK(4)
+        __syncwarp();
+        // Report the indices through the map one round late: ONE load instruction per round,
+        // issued after the loop (a load per pick into the same register would serialise on the
+        // register scoreboard at L2 latency), consumed by the store at the top of the next D.
+        if (w == 0 && pend_slot >= 0) pend_val = pmap[e.y];
+        if (TRACE) {
+            tr[6] = clock64();
+            tr[7] = K | (nupd << 8);
+            if (blockIdx.x == 0 && lane == 0 && trace)
+                for (int q = 0; q < 8; ++q) trace[((size_t)(rounds - 1) * NW + w) * 8 + q] = tr[q];
+        }
+        j += K;
+        if (j >= m) {   // the very last sample is never applied (the reference stops after writing it)
+            --K;
+            if (K == 0) break;
+        }
     }
-    if (tid == 0) out[m - 1] = (int)pending;
-#undef PDM_TICK
-    if (PROF && lane == 0 && prof) {
-        pc[7] = clock64() - tq0;
-        for (int q = 0; q < 8; ++q) prof[((size_t)blockIdx.x * NW + w) * 8 + q] = pc[q];
-    }
+    if (w == 0 && pend_slot >= 0) out[pend_slot] = (int)pend_val;
+    if (stats && tid == 0) stats[blockIdx.x] = rounds;
 
     // ---- 5. leave temp as the reference does: running minima in original order ------------
     __syncthreads();
     unsigned ko[BPW];
 #pragma unroll
-    for (int j = 0; j < BPW; ++j) {
-        const int pos = ((j * NW + w) << 5) + lane;
-        ko[j] = pos < n ? pmap[pos] : 0u;
+    for (int jq = 0; jq < BPW; ++jq) {
+        const int pos = ((jq * NW + w) << 5) + lane;
+        ko[jq] = pos < n ? pmap[pos] : 0u;
     }
     __syncthreads();  // all map entries are read before any of them is overwritten
 #pragma unroll
-    for (int j = 0; j < BPW; ++j) {
-        const int pos = ((j * NW + w) << 5) + lane;
-        if (pos < n) tmp[ko[j]] = t[j];
+    for (int jq = 0; jq < BPW; ++jq) {
+        const int pos = ((jq * NW + w) << 5) + lane;
+        if (pos < n) tmp[ko[jq]] = t[jq];
     }
 }
 
-template <int NW, int BPW>
+template <int NW, int BPW, int KMAX>
 static int launch_bucket(int b, int n, int m, int p, const float *xyz, float *temp, int *idx,
-                         cudaStream_t st) {
-    using L = FpsSmem<NW, BPW>;
-    auto kern = fps_bucket_kernel<NW, BPW>;
+                         int *stats, cudaStream_t st) {
+    using L = FpsSmem<NW, BPW, KMAX>;
+    auto kern = fps_bucket_kernel<NW, BPW, KMAX>;
     // per launch (a few hundred ns): the attribute is per device, and one process may drive several
     PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
-    kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, nullptr);
+    kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, stats, nullptr);
     count_launch();
     PDM_CHECK_LAUNCH("farthest_point_sampling(bucket)");
     return PDM_OK;
 }
 
-// capacity (points) -> kernel with `nw` warps; returns PDM_ERR_UNSUPPORTED for combinations
-// that do not exist (BPW must stay within 1..32)
+// capacity (points) -> kernel with `nw` warps and up to `kmax` samples per round; returns
+// PDM_ERR_UNSUPPORTED for combinations that are not instantiated
 template <int CAP>
-static int launch_cap(int nw, int b, int n, int m, int p, const float *xyz, float *temp, int *idx,
-                      cudaStream_t st) {
-    switch (nw) {
-#define PDM_NW(NWV)                                                                    \
-    case NWV:                                                                          \
-        if constexpr (CAP / (32 * NWV) >= 1 && CAP / (32 * NWV) <= 32)                 \
-            return launch_bucket<NWV, CAP / (32 * NWV)>(b, n, m, p, xyz, temp, idx, st); \
-        break;
-        PDM_NW(4) PDM_NW(8) PDM_NW(16) PDM_NW(32)
-#undef PDM_NW
-        default: break;
+static int launch_cap(int nw, int kmax, int b, int n, int m, int p, const float *xyz, float *temp,
+                      int *idx, int *stats, cudaStream_t st) {
+#define PDM_TRY(NWV, KV)                                                                  \
+    if (nw == NWV && kmax == KV) {                                                        \
+        if constexpr (CAP / (32 * NWV) >= 1 && CAP / (32 * NWV) <= 32)                    \
+            return launch_bucket<NWV, CAP / (32 * NWV), KV>(b, n, m, p, xyz, temp, idx, stats, st); \
     }
-    return fail(PDM_ERR_UNSUPPORTED, "farthest_point_sampling: no bucket kernel for cap %d with %d warps", CAP, nw);
+    PDM_TRY(16, 8) PDM_TRY(16, 1) PDM_TRY(8, 8) PDM_TRY(16, 4) PDM_TRY(16, 12)
+#undef PDM_TRY
+    return fail(PDM_ERR_UNSUPPORTED, "farthest_point_sampling: no bucket kernel for cap %d, %d warps, kmax %d",
+                CAP, nw, kmax);
+}
+
+static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, int *stats,
+                        cudaStream_t st) {
+    const int bs = ref_fps_block_size(n);
+    int p = 0;
+    while ((1 << p) < bs) ++p;
+    const char *force = getenv("PDM_FPS_KERNEL");  // "generic" | unset (debug/testing knob)
+    const bool generic = force && force[0] == 'g';
+    if (!generic && n >= 512 && n <= 16384) {
+        // warps per CTA / samples per round: tuned on B200; PDM_FPS_NW / PDM_FPS_KMAX override
+        const char *nwenv = getenv("PDM_FPS_NW"), *kenv = getenv("PDM_FPS_KMAX");
+        const int nw = nwenv ? atoi(nwenv) : 16;
+        const int km = kenv ? atoi(kenv) : 8;
+        if (n <= 1024) return launch_cap<1024>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
+        if (n <= 2048) return launch_cap<2048>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
+        if (n <= 4096) return launch_cap<4096>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
+        if (n <= 8192) return launch_cap<8192>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
+        return launch_cap<16384>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
+    }
+    fps_generic_kernel<1024><<<b, 1024, 0, st>>>(n, m, p, xyz, temp, idx);
+    count_launch();
+    PDM_CHECK_LAUNCH("farthest_point_sampling(generic)");
+    return PDM_OK;
 }
 
 }  // namespace pdm
 
-// Debug-only entry (not part of include/pdm_ops.h): per-phase cycle counters of the bucket
-// kernel, prof = device buffer of b*16*8 long long.  16384-point and 4096-point frames only.
-extern "C" int pdm_debug_fps_profile(int b, int n, int m, const float *xyz, float *temp, int *idx,
-                                     long long *prof, void *stream) {
+// Debug-only entry: timestamp trace of frame 0 (16384-point frames, <16,32,8> kernel).
+extern "C" int pdm_debug_fps_trace(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                   int *stats, long long *trace, void *stream) {
     using namespace pdm;
-    const int bs = ref_fps_block_size(n);
+    if (n <= 8192 || n > 16384) return fail(PDM_ERR_UNSUPPORTED, "debug_fps_trace: n=%d", n);
     int p = 0;
-    while ((1 << p) < bs) ++p;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (n > 4096 && n <= 16384) {
-        using L = FpsSmem<16, 32>;
-        auto kern = fps_bucket_kernel<16, 32, true>;
-        PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
-        kern<<<b, 512, L::kBytes, st>>>(n, m, p, xyz, temp, idx, prof);
-    } else if (n <= 4096 && n > 2048) {
-        using L = FpsSmem<16, 8>;
-        auto kern = fps_bucket_kernel<16, 8, true>;
-        PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
-        kern<<<b, 512, L::kBytes, st>>>(n, m, p, xyz, temp, idx, prof);
-    } else {
-        return fail(PDM_ERR_UNSUPPORTED, "debug_fps_profile: n=%d", n);
-    }
-    PDM_CHECK_LAUNCH("debug_fps_profile");
+    while ((1 << p) < ref_fps_block_size(n)) ++p;
+    using L = FpsSmem<16, 32, 8>;
+    auto kern = fps_bucket_kernel<16, 32, 8, true>;
+    PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+    kern<<<b, 512, L::kBytes, (cudaStream_t)stream>>>(n, m, p, xyz, temp, idx, stats, trace);
+    PDM_CHECK_LAUNCH("debug_fps_trace");
     return PDM_OK;
+}
+
+// Debug-only entry (not part of include/pdm_ops.h): like pdm_farthest_point_sampling, and also
+// writes the number of barrier rounds each frame needed into stats[b] (device ints).
+extern "C" int pdm_debug_fps_rounds(int b, int n, int m, const float *xyz, float *temp, int *idx,
+                                    int *stats, void *stream) {
+    return pdm::fps_dispatch(b, n, m, xyz, temp, idx, stats, (cudaStream_t)stream);
 }
 
 extern "C" int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp,
@@ -518,26 +631,5 @@ extern "C" int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz
     if (n == 0) return fail(PDM_ERR_INVALID_ARG, "farthest_point_sampling: n == 0 with m > 0");
     if (!xyz || !temp || !idx) return fail(PDM_ERR_INVALID_ARG, "farthest_point_sampling: null pointer");
     if ((long long)n * 3 > 0x7fffffffLL) return fail(PDM_ERR_UNSUPPORTED, "farthest_point_sampling: n too large");
-    cudaStream_t st = (cudaStream_t)stream;
-    const int bs = ref_fps_block_size(n);
-    int p = 0;
-    while ((1 << p) < bs) ++p;
-    const char *force = getenv("PDM_FPS_KERNEL");  // "generic" | unset (debug/testing knob)
-    const bool generic = force && force[0] == 'g';
-    if (!generic && n >= 512 && n <= 16384) {
-        // warps per CTA: few warps keep the per-round issue + barrier cost low, enough warps
-        // keep the (few) surviving bucket updates of a round in different warps.  Tuned on B200;
-        // PDM_FPS_NW overrides for experiments.
-        const char *nwenv = getenv("PDM_FPS_NW");
-        int nw = nwenv ? atoi(nwenv) : 0;
-        if (n <= 1024) return launch_cap<1024>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
-        if (n <= 2048) return launch_cap<2048>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
-        if (n <= 4096) return launch_cap<4096>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
-        if (n <= 8192) return launch_cap<8192>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
-        return launch_cap<16384>(nw ? nw : 16, b, n, m, p, xyz, temp, idx, st);
-    }
-    fps_generic_kernel<1024><<<b, 1024, 0, st>>>(n, m, p, xyz, temp, idx);
-    count_launch();
-    PDM_CHECK_LAUNCH("farthest_point_sampling(generic)");
-    return PDM_OK;
+    return fps_dispatch(b, n, m, xyz, temp, idx, nullptr, (cudaStream_t)stream);
 }
