@@ -90,6 +90,23 @@ int pdm_three_interpolate(int b, int c, int m, int n, const float *points, const
 int pdm_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                const float *weight, float *grad_points, void *stream);
 
+/* ---- PDM neck (SPEC_PDM.md) ---------------------------------------------------------- */
+
+/* Point dilation + SH/Gaussian feature filling + multi-centre fusion + height compression.
+ * The reference tree has NO code for this stage, so there is no reference
+ * binding to cite; the entry implements SPEC_PDM.md and fills the pcdet `map_to_bev` slot
+ * (detector3d_template.py:85-95; output contract of height_compression.py:22-25).
+ *   point_coords (P,4) [b,x,y,z] grouped by b ascending, point_features (P,C),
+ *   coef (P,(sh_degree+1)^2) per-centre SH coefficients,
+ *   range_min[3], voxel[3], grid[3]=(X,Y,Z), dilation[3]=(kx,ky,kz) host arrays,
+ *   -> spatial_features (B,C,Y,X), every element written (zeros for empty pillars).
+ * dbg_keys / dbg_w (optional, may be NULL): (P,K) int32 cell keys (-1 = dropped) and fp32 weights
+ * of every (centre, offset) entry, K = (2kx+1)(2ky+1)(2kz+1), for parity tests. */
+int pdm_neck_forward(int batch, int p, int c, const float *point_coords, const float *point_features,
+                     const float *coef, const float *range_min, const float *voxel, const int *grid,
+                     const int *dilation, int sh_degree, float sigma, float eps,
+                     float *spatial_features, int *dbg_keys, float *dbg_w, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
