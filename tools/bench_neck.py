@@ -1,0 +1,55 @@
+"""BASELINE configs[0]: the PDM neck alone (4096 centres x 256 channels, batch 1 by default) --
+CUDA path vs the pure-torch CPU oracle.  Prints one JSON line with per-kernel byte accounting."""
+import argparse, json, os, sys, time
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import pdm_neck_oracle as O
+from pdm_ssd_b200 import pdm_neck, synthetic, _lib
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--centres", type=int, default=4096)
+ap.add_argument("--channels", type=int, default=256)
+ap.add_argument("--iters", type=int, default=50)
+ap.add_argument("--no-cpu", action="store_true")
+a = ap.parse_args()
+RANGE, VOX = [0.0, -40.0, -3.0, 70.4, 40.0, 1.0], [0.4, 0.4, 0.4]
+grid = O.grid_size(RANGE, VOX)
+dev = torch.device("cuda:0")
+import oracle
+rows = []
+for b in range(a.batch):
+    fr = synthetic.kitti_frame(1000 + b)[None, :, :3].copy()
+    idx = oracle.fps(fr, a.centres)[0]           # centres = FPS output of a synthetic frame
+    rows.append(np.concatenate([np.full((a.centres, 1), b, np.float32), fr[0][idx]], 1))
+coords = torch.from_numpy(np.concatenate(rows, 0))
+feats = torch.randn(a.batch * a.centres, a.channels, generator=torch.Generator().manual_seed(7))
+coef = torch.randn(a.batch * a.centres, 9, generator=torch.Generator().manual_seed(8)) * 0.5
+dc, df, dco = coords.to(dev), feats.to(dev), coef.to(dev)
+for _ in range(5):
+    out = pdm_neck.neck_forward(dc, df, dco, a.batch, RANGE, VOX, grid)
+torch.cuda.synchronize()
+_lib.reset_launch_count()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.iters):
+    out = pdm_neck.neck_forward(dc, df, dco, a.batch, RANGE, VOX, grid)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / a.iters
+out_bytes = out.numel() * 4
+in_bytes = (coords.numel() + feats.numel()) * 4
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+line = {"workload": "configs[0]: PDM neck alone, %d centres x %d ch, batch %d, grid %s, dilation 3x3x3, SH degree 2" % (a.centres, a.channels, a.batch, grid),
+        "gpu_ms": ms, "frames_per_s": a.batch / (ms * 1e-3), "launches_per_call": _lib.launch_count() / a.iters,
+        "algorithmic_bytes": in_bytes + out_bytes, "achieved_gbs": (in_bytes + out_bytes) / (ms * 1e-3) / 1e9,
+        "hbm_frac": (in_bytes + out_bytes) / (ms * 1e-3) / 1e9 / peak}
+if not a.no_cpu:
+    torch.set_num_threads(os.cpu_count())
+    O.neck_forward(coords, feats, coef, a.batch, RANGE, VOX)
+    t0 = time.perf_counter()
+    want = O.neck_forward(coords, feats, coef, a.batch, RANGE, VOX)
+    line["cpu_torch_ms"] = (time.perf_counter() - t0) * 1e3
+    line["cpu_cores"] = os.cpu_count()
+    line["max_rel_err"] = float((out.cpu() - want).abs().max() / want.abs().max())
+print(json.dumps(line))
