@@ -90,6 +90,24 @@ int pdm_three_interpolate(int b, int c, int m, int n, const float *points, const
 int pdm_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                const float *weight, float *grad_points, void *stream);
 
+/* ---- fused set-abstraction scale ---------------------------------------------------------- */
+
+/* One scale of _PointnetSAModuleBase.forward in a single kernel (inference): replaces
+ * QueryAndGroup.forward after the ball query (pointnet2_utils.py:250-257: group xyz, subtract the
+ * centre, group features, cat), the shared MLP `self.mlps[i]` (Conv2d 1x1 bias=False + BatchNorm2d
+ * (eval) + ReLU per layer, pointnet2_modules.py:40,90-97) and the max-pool over nsample
+ * (pointnet2_modules.py:41-52).
+ *   xyz (B,N,3), features (B,c_feat,N) or NULL when c_feat == 0, new_xyz (B,M,3),
+ *   idx (B,M,nsample) from pdm_ball_query; widths[n_layers+1] host array with
+ *   widths[0] = 3*use_xyz + c_feat; packed = per layer l the BN-folded weights transposed
+ *   Wt[k][pad4(widths[l+1])] (k < widths[l], zero-padded columns) followed by the folded bias
+ *   [pad4(widths[l+1])], all layers back to back (device, fp32)
+ *   -> out (B, widths[n_layers], M).
+ * Limits: n_layers <= 4, every width <= 128, nsample a power of two in 4..128. */
+int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample, int use_xyz, const float *xyz,
+                         const float *features, const float *new_xyz, const int *idx, int n_layers,
+                         const int *widths, const float *packed, float *out, void *stream);
+
 /* ---- PDM neck (SPEC_PDM.md) ---------------------------------------------------------- */
 
 /* Point dilation + SH/Gaussian feature filling + multi-centre fusion + height compression.

@@ -10,7 +10,44 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import pointnet2_utils
+from . import _lib, pointnet2_utils
+
+# Inference fast path: ball query + ONE fused kernel per scale (grouping + shared MLP + max-pool,
+# csrc/sa_fused.cu) instead of group / sub / cat / conv / bn / relu / pool.  Used only in eval mode
+# without autograd, with our native backend, and when the scale fits the kernel's limits;
+# otherwise the reference-shaped path below runs.  Set to False to force that path.
+ENABLE_FUSED_SA = True
+
+
+def _fold_mlp(mlp: nn.Sequential):
+    """[(W' (out,in), b' (out))] with eval-mode BatchNorm folded into the 1x1 conv, or None when the
+    Sequential is not the Conv2d(1x1,bias=False)+BatchNorm2d+ReLU pattern of pointnet2_modules.py:90-97."""
+    layers = list(mlp)
+    if len(layers) == 0 or len(layers) % 3 != 0:
+        return None
+    folded = []
+    for conv, bn, act in zip(layers[0::3], layers[1::3], layers[2::3]):
+        if not (isinstance(conv, nn.Conv2d) and isinstance(bn, nn.BatchNorm2d) and isinstance(act, nn.ReLU)):
+            return None
+        if conv.kernel_size != (1, 1) or conv.bias is not None or not bn.track_running_stats or not bn.affine:
+            return None
+        scale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+        folded.append((conv.weight[:, :, 0, 0] * scale[:, None], bn.bias - bn.running_mean * scale))
+    return folded
+
+
+def _pack_folded(folded):
+    """Layout expected by pdm_sa_fused_forward: per layer Wt[k][pad4(out)] then bias[pad4(out)]."""
+    chunks, widths = [], [folded[0][0].shape[1]]
+    for w, b in folded:
+        out_c, pad = w.shape[0], (w.shape[0] + 3) // 4 * 4
+        wt = w.new_zeros((w.shape[1], pad))
+        wt[:, :out_c] = w.t()
+        bp = b.new_zeros(pad)
+        bp[:out_c] = b
+        chunks += [wt.reshape(-1), bp]
+        widths.append(out_c)
+    return torch.cat(chunks).contiguous(), widths
 
 
 def _shared_mlp(widths: List[int]) -> nn.Sequential:
@@ -47,10 +84,58 @@ class _PointnetSAModuleBase(nn.Module):
             channels_first = xyz.transpose(1, 2).contiguous()
             new_xyz = pointnet2_utils.gather_operation(channels_first, sample_idx).transpose(1, 2).contiguous()
         pooled = []
-        for grouper, mlp in zip(self.groupers, self.mlps):
+        for si, (grouper, mlp) in enumerate(zip(self.groupers, self.mlps)):
+            fused = self._fused_scale(si, grouper, mlp, xyz, new_xyz, features)
+            if fused is not None:
+                pooled.append(fused)
+                continue
             grouped = grouper(xyz, new_xyz, features)          # (B, C_in, npoint, nsample)
             pooled.append(self._pool(mlp(grouped)).squeeze(-1))  # (B, C_out, npoint)
         return new_xyz, torch.cat(pooled, dim=1)
+
+    def _fused_scale(self, si, grouper, mlp, xyz, new_xyz, features):
+        """(B, C_out, npoint) through csrc/sa_fused.cu, or None when the fast path does not apply."""
+        if not ENABLE_FUSED_SA or self.training or torch.is_grad_enabled() or self.pool_method != 'max_pool':
+            return None
+        if not isinstance(grouper, pointnet2_utils.QueryAndGroup) or not xyz.is_cuda:
+            return None
+        if pointnet2_utils.get_backend() is not pointnet2_utils._native:
+            return None
+        S = grouper.nsample
+        if S < 4 or S > 128 or (S & (S - 1)) != 0 or (features is None and not grouper.use_xyz):
+            return None
+        version = sum(p._version for p in mlp.parameters()) + sum(b._version for b in mlp.buffers())
+        cache = self.__dict__.setdefault('_fused_cache', {})
+        hit = cache.get(si)
+        if hit is None or hit[0] != version or hit[1].device != xyz.device:
+            folded = _fold_mlp(mlp)
+            if folded is None or len(folded) > 4 or max(max(w.shape) for w, _ in folded) > 128:
+                cache[si] = (version, xyz.new_zeros(1), None)
+            else:
+                packed, widths = _pack_folded([(w.detach().float(), b.detach().float()) for w, b in folded])
+                cache[si] = (version, packed.to(xyz.device), widths)
+            hit = cache[si]
+        _, packed, widths = hit
+        if widths is None:
+            return None
+        B, N, _ = xyz.shape
+        M = new_xyz.shape[1]
+        c_feat = 0 if features is None else features.shape[1]
+        if widths[0] != (3 if grouper.use_xyz else 0) + c_feat:
+            return None
+        idx = pointnet2_utils.ball_query(grouper.radius, S, xyz, new_xyz)
+        out = torch.empty((B, widths[-1], M), dtype=torch.float32, device=xyz.device)
+        feats = features.contiguous() if features is not None else None
+        import ctypes
+        warr = (ctypes.c_int * len(widths))(*widths)
+        with torch.cuda.device(xyz.device):
+            rc = _lib.load().pdm_sa_fused_forward(
+                B, N, M, c_feat, S, 1 if grouper.use_xyz else 0, xyz.data_ptr(),
+                feats.data_ptr() if feats is not None else None, new_xyz.data_ptr(), idx.data_ptr(),
+                len(widths) - 1, warr, packed.data_ptr(), out.data_ptr(),
+                torch.cuda.current_stream(xyz.device).cuda_stream)
+        _lib.check(rc, "pdm_sa_fused_forward")
+        return out
 
 
 class PointnetSAModuleMSG(_PointnetSAModuleBase):

@@ -18,12 +18,19 @@ def _fp32():
     torch.backends.cudnn.allow_tf32 = False
 
 
+@pytest.fixture
+def unfused(monkeypatch):
+    """Reference-shaped path (group / conv / bn / relu / pool as separate ops): bit-comparable with
+    the same host code over the reference kernels."""
+    monkeypatch.setattr(M, "ENABLE_FUSED_SA", False)
+
+
 def _points(B, N, first=0):
     fr = synthetic.kitti_batch(B, N, first_frame=first)
     return torch.from_numpy(synthetic.to_pcdet_points(fr)).to(DEV)
 
 
-def test_sa_and_fp_modules_match_reference_kernels(ref_ext):
+def test_sa_and_fp_modules_match_reference_kernels(ref_ext, unfused):
     if ref_ext is None:
         pytest.skip("oracle/_ref not built")
     torch.manual_seed(0)
@@ -42,7 +49,7 @@ def test_sa_and_fp_modules_match_reference_kernels(ref_ext):
         assert torch.equal(a, b)
 
 
-def test_pointnet2msg_backbone_matches_reference_kernels(ref_ext):
+def test_pointnet2msg_backbone_matches_reference_kernels(ref_ext, unfused):
     if ref_ext is None:
         pytest.skip("oracle/_ref not built")
     cfg = AttrDict(SA_CONFIG=dict(NPOINTS=[1024, 256], RADIUS=[[0.5, 1.0], [1.0, 2.0]], NSAMPLE=[[16, 32], [16, 32]],
@@ -83,3 +90,54 @@ def test_detector_end_to_end_shapes_determinism_and_frame_independence():
         d1 = model({"batch_size": 1, "points": one})["detections"]
         torch.testing.assert_close(d1[0, :, :8], det[f, :, :8], rtol=1e-3, atol=1e-4)
     assert gather_detections(det) is det                      # no process group: identity
+
+
+def _randomise_bn(module, seed):
+    g = torch.Generator().manual_seed(seed)
+    for m in module.modules():
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.running_mean.copy_(torch.randn(m.num_features, generator=g) * 0.2)
+            m.running_var.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.weight.data.copy_(torch.rand(m.num_features, generator=g) + 0.5)
+            m.bias.data.copy_(torch.randn(m.num_features, generator=g) * 0.1)
+
+
+@pytest.mark.parametrize("N,M_,C,S,mlp,use_xyz", [
+    (16384, 4096, 1, 32, [1, 16, 16, 32], True),        # SA1 of the KITTI chain
+    (4096, 1024, 64, 32, [64, 64, 64, 128], True),      # SA2
+    (4096, 1023, 8, 16, [8, 18, 30], True),             # widths not multiples of 4, ragged last CTA
+    (2048, 300, 5, 64, [5, 32], False),                 # one layer, no xyz channels
+    (2048, 77, 0, 128, [0, 24, 24, 24, 40], True),      # xyz only, four layers, one centre per CTA
+    (1024, 64, 3, 4, [3, 128], True),                   # tiny groups, widest layer
+])
+def test_fused_sa_scale_matches_unfused_path(N, M_, C, S, mlp, use_xyz, monkeypatch):
+    torch.manual_seed(N + S)
+    sa = M.PointnetSAModuleMSG(npoint=M_, radii=[1.2], nsamples=[S], mlps=[list(mlp)], use_xyz=use_xyz).to(DEV).eval()
+    _randomise_bn(sa, S)
+    pts = _points(2, N, first=S).view(2, N, 5)
+    xyz = pts[..., 1:4].contiguous()
+    feat = torch.randn(2, C, N, device=DEV) if C > 0 else None
+    with torch.no_grad():
+        nx1, fused = sa(xyz, feat)
+        monkeypatch.setattr(M, "ENABLE_FUSED_SA", False)
+        nx2, ref = sa(xyz, feat)
+    assert torch.equal(nx1, nx2) and fused.shape == ref.shape == (2, mlp[-1], M_)
+    err = float((fused - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
+    assert err < 1e-5, err          # budget of north_star: 1e-3 relative
+
+
+def test_fused_path_is_skipped_when_it_must_be():
+    sa = M.PointnetSAModuleMSG(npoint=64, radii=[1.0], nsamples=[12], mlps=[[1, 8]]).to(DEV).eval()   # nsample not a power of 2
+    pts = _points(1, 1024).view(1, 1024, 5)
+    xyz, feat = pts[..., 1:4].contiguous(), pts[..., 4:].transpose(1, 2).contiguous()
+    with torch.no_grad():
+        _, out = sa(xyz, feat)
+    assert out.shape == (1, 8, 64)
+    sa2 = M.PointnetSAModuleMSG(npoint=64, radii=[1.0], nsamples=[16], mlps=[[1, 8]], pool_method='avg_pool').to(DEV).eval()
+    with torch.no_grad():
+        _, out2 = sa2(xyz, feat)
+    assert out2.shape == (1, 8, 64)
+    sa3 = M.PointnetSAModuleMSG(npoint=64, radii=[1.0], nsamples=[16], mlps=[[1, 8]]).to(DEV).train()
+    _, out3 = sa3(xyz, feat)                      # training: autograd path
+    out3.sum().backward()
+    assert sa3.mlps[0][0].weight.grad is not None
