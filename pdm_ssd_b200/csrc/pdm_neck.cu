@@ -8,7 +8,8 @@
 //
 // Pipeline (one stream, no host sync, no atomics on floating-point data):
 //   pdm_emit_kernel     thread per (centre, offset): cell, key3, weight w; histogram of key3
-//   pdm_scan_kernel     CTA per frame: exclusive scan of the per-cell counts, frame totals
+//   pdm_scan_kernel     CTA per 4096-cell chunk: exclusive scan of the per-cell counts (chunk bases
+//                       from per-chunk counts the emit kernel accumulates), frame totals
 //   pdm_scatter_kernel  entry ids bucketed by cell (order inside a cell is arbitrary here ...)
 //   pdm_bev_kernel      CTA per (frame, y, 32-wide x tile), warp per pillar: walks the pillar's
 //                       cells in ascending z and each cell's entries in ASCENDING ENTRY ID
@@ -31,13 +32,14 @@ struct NeckCfg {
     float eps;
 };
 
+constexpr int kScanChunkFwd = 4096;
 constexpr float kSH0 = 0.28209479177387814f, kSH1 = 0.4886025119029199f, kSH2 = 1.0925484305920792f,
                 kSH3 = 0.31539156525252005f, kSH4 = 0.5462742152960396f;
 
 __global__ void __launch_bounds__(256)
 pdm_emit_kernel(int p_total, int K, int nsh, NeckCfg cfg, const float *__restrict__ coords,
                 const float *__restrict__ coef, int *__restrict__ keys, float *__restrict__ wts,
-                int *__restrict__ count) {
+                int *__restrict__ count, int *__restrict__ chunk_count, int chunks_per_frame) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (long long)p_total * K) return;
     const int p = (int)(e / K), o = (int)(e % K);
@@ -87,58 +89,65 @@ pdm_emit_kernel(int p_total, int K, int nsh, NeckCfg cfg, const float *__restric
         }
         w = __fmul_rn(acc, expf(__fdiv_rn(-r2, cfg.two_sigma2)));
         atomicAdd(&count[key], 1);
+        const int cpf = cfg.grid[0] * cfg.grid[1] * cfg.grid[2];
+        atomicAdd(&chunk_count[b * chunks_per_frame + (key - b * cpf) / kScanChunkFwd], 1);
     }
     keys[e] = key;
     wts[e] = w;
 }
 
-// exclusive scan of one frame's cell counts, in place; frame total to totals[frame]
-constexpr int kScanThreads = 1024;
+// Exclusive scan of the per-cell counts, in place and per frame.  The emit kernel also counts the
+// entries of every chunk of kScanChunk cells (chunk_count), so each CTA can scan one chunk
+// independently: its base is the sum of the earlier chunks of its frame.  CTA (chunk, frame).
+constexpr int kScanThreads = 256;
+constexpr int kScanChunk = kScanChunkFwd;   // cells per CTA: 16 per thread
 __global__ void __launch_bounds__(kScanThreads)
-pdm_scan_kernel(int cells_per_frame, int *__restrict__ count, int *__restrict__ totals) {
+pdm_scan_kernel(int cells_per_frame, int chunks_per_frame, int *__restrict__ count,
+                const int *__restrict__ chunk_count, int *__restrict__ totals) {
     __shared__ int wsum[kScanThreads / 32];
-    __shared__ int carry, tile_total;
+    __shared__ int base_s;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    int *c = count + (size_t)blockIdx.x * cells_per_frame;
-    if (tid == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < cells_per_frame; base += 4 * kScanThreads) {
-        const int c0 = base + tid * 4;
-        int v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (c0 + q < cells_per_frame) ? c[c0 + q] : 0;
-        const int tsum = v[0] + v[1] + v[2] + v[3];
-        int incl = tsum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += y;
+    const int chunk = blockIdx.x, frame = blockIdx.y;
+    const int *cc = chunk_count + (size_t)frame * chunks_per_frame;
+    if (w == 0) {  // base = entries of the earlier chunks of this frame (and the frame total, once)
+        int s = 0, all = 0;
+        for (int q = lane; q < chunks_per_frame; q += 32) {
+            const int v = __ldg(cc + q);
+            all += v;
+            if (q < chunk) s += v;
         }
-        if (lane == 31) wsum[w] = incl;
-        __syncthreads();
-        if (w == 0) {
-            const int s = wsum[lane];
-            int si = s;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, si, o);
-                if (lane >= o) si += y;
-            }
-            wsum[lane] = si - s;
-            if (lane == 31) tile_total = si;
+        s = __reduce_add_sync(0xffffffffu, s);
+        all = __reduce_add_sync(0xffffffffu, all);
+        if (lane == 0) {
+            base_s = s;
+            if (chunk == 0) totals[frame] = all;
         }
-        __syncthreads();
-        int run = carry + wsum[w] + incl - tsum;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (c0 + q < cells_per_frame) c[c0 + q] = run;
-            run += v[q];
-        }
-        __syncthreads();
-        if (tid == 0) carry += tile_total;
-        __syncthreads();
     }
-    if (tid == 0) totals[blockIdx.x] = carry;
+    int *c = count + (size_t)frame * cells_per_frame + (size_t)chunk * kScanChunk;
+    const int ncell = min(kScanChunk, cells_per_frame - chunk * kScanChunk);
+    constexpr int PER = kScanChunk / kScanThreads;
+    int v[PER];
+    int tsum = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        v[q] = (tid * PER + q < ncell) ? c[tid * PER + q] : 0;
+        tsum += v[q];
+    }
+    int incl = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) wsum[w] = incl;
+    __syncthreads();
+    int run = base_s + incl - tsum;
+    for (int q = 0; q < w; ++q) run += wsum[q];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        if (tid * PER + q < ncell) c[tid * PER + q] = run;
+        run += v[q];
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -266,7 +275,8 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
     auto align = [](size_t v) { return (v + 255) / 256 * 256; };
     const size_t sz_keys = align((size_t)n_entries * 4 + 4), sz_w = sz_keys, sz_sorted = sz_keys;
     const size_t sz_count = align((size_t)cells_per_frame * batch * 4);
-    const size_t sz_tot = align((size_t)batch * 4);
+    const int chunks_per_frame = (int)((cells_per_frame + kScanChunk - 1) / kScanChunk);
+    const size_t sz_tot = align((size_t)batch * 4) + align((size_t)batch * chunks_per_frame * 4);
     char *ws = nullptr;
     PDM_CHECK_CUDA(cudaMallocAsync((void **)&ws, sz_keys + sz_w + sz_sorted + sz_count + sz_tot, st));
     int *keys = dbg_keys ? dbg_keys : reinterpret_cast<int *>(ws);
@@ -274,15 +284,17 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
     int *sorted = reinterpret_cast<int *>(ws + sz_keys + sz_w);
     int *count = reinterpret_cast<int *>(ws + sz_keys + sz_w + sz_sorted);
     int *totals = reinterpret_cast<int *>(ws + sz_keys + sz_w + sz_sorted + sz_count);
+    int *chunk_count = reinterpret_cast<int *>(ws + sz_keys + sz_w + sz_sorted + sz_count + align((size_t)batch * 4));
     cudaError_t err = cudaMemsetAsync(count, 0, sz_count + sz_tot, st);
     if (err == cudaSuccess && n_entries > 0) {
         pdm_emit_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(p, K, nsh, cfg, point_coords, coef, keys,
-                                                                           wts, count);
+                                                                           wts, count, chunk_count, chunks_per_frame);
         count_launch();
         err = cudaGetLastError();
     }
     if (err == cudaSuccess) {
-        pdm_scan_kernel<<<batch, kScanThreads, 0, st>>>((int)cells_per_frame, count, totals);
+        pdm_scan_kernel<<<dim3(chunks_per_frame, batch), kScanThreads, 0, st>>>((int)cells_per_frame, chunks_per_frame,
+                                                                               count, chunk_count, totals);
         count_launch();
         err = cudaGetLastError();
     }

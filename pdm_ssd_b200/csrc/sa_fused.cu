@@ -34,17 +34,21 @@ struct SAFusedParams {
     int wpad[kSAMaxLayers + 1];    // width rounded up to a multiple of 4
     int woff[kSAMaxLayers];        // offset (floats) of layer l's transposed weights Wt[k][wpad] in `packed`
     int boff[kSAMaxLayers];        // offset of its bias (wpad floats)
+    int act_floats;                // size of one activation buffer: max padded width * kSARows
+    int w_floats;                  // size of the weight buffer: max_l width[l] * wpad[l+1]
 };
 
-__global__ void __launch_bounds__(kSAThreads, 1)
+__global__ void __launch_bounds__(kSAThreads)
 sa_fused_kernel(SAFusedParams P, const float *__restrict__ xyz, const float *__restrict__ feats,
                 const float *__restrict__ new_xyz, const int *__restrict__ idx,
                 const float *__restrict__ packed, float *__restrict__ out) {
     extern __shared__ __align__(16) float smem[];
-    float *bufA = smem;                           // [kSAMaxC][kSARows]
-    float *bufB = bufA + kSAMaxC * kSARows;       // [kSAMaxC][kSARows]
-    float *wsm = bufB + kSAMaxC * kSARows;        // [k][wpad] of the current layer (<= 128*128? no: <= kSAMaxC*kSAMaxC)
-    float *bsm = wsm + kSAMaxC * kSAMaxC;         // [wpad]
+    // sized by the host for THIS scale's widths: narrow MLPs (SA1: 4-16-16-32) take ~37 KB and
+    // several CTAs share an SM, wide ones (128 channels) take the full 193 KB
+    float *bufA = smem;                           // [max width][kSARows]
+    float *bufB = bufA + P.act_floats;            // [max width][kSARows]
+    float *wsm = bufB + P.act_floats;             // [k][wpad] of the current layer
+    float *bsm = wsm + P.w_floats;                // [wpad]
     const int tid = threadIdx.x;
     const int bi = blockIdx.y;
     const int S = P.nsample;
@@ -180,15 +184,20 @@ extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample
         P.width[l] = widths[l];
         P.wpad[l] = (widths[l] + 3) / 4 * 4;
     }
+    int maxw = 0, maxwt = 0;
+    for (int l = 0; l <= n_layers; ++l) maxw = P.wpad[l] > maxw ? P.wpad[l] : maxw;
     for (int l = 0; l < n_layers; ++l) {
         P.woff[l] = off; off += P.width[l] * P.wpad[l + 1];
         P.boff[l] = off; off += P.wpad[l + 1];
+        maxwt = P.width[l] * P.wpad[l + 1] > maxwt ? P.width[l] * P.wpad[l + 1] : maxwt;
     }
+    P.act_floats = maxw * kSARows;
+    P.w_floats = (maxwt + 3) / 4 * 4;
     if (b == 0 || m == 0) return PDM_OK;
     if (!xyz || !new_xyz || !idx || !packed || !out || (c_feat > 0 && !features))
         return fail(PDM_ERR_INVALID_ARG, "sa_fused_forward: null pointer");
     if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "sa_fused_forward: batch > 65535");
-    const size_t smem = sizeof(float) * ((size_t)2 * kSAMaxC * kSARows + (size_t)kSAMaxC * kSAMaxC + kSAMaxC);
+    const size_t smem = sizeof(float) * ((size_t)2 * P.act_floats + P.w_floats + kSAMaxC);
     PDM_CHECK_CUDA(cudaFuncSetAttribute(sa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int cpb = kSARows / nsample;
     dim3 grid((m + cpb - 1) / cpb, b);
