@@ -10,7 +10,11 @@ Frames are independent, so ranks just take different frames ("weak" scaling, no 
 collective); the only collective is the max-reduction of the timing.
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events on the launch
-stream); `e2e` is the same through host pinned buffers with H2D/D2H inside the timed region;
+stream) with STREAMS batches in flight: the steps go round-robin to STREAMS CUDA streams, each
+replaying a CUDA graph of one step (one batch keeps only ~16 of 148 SMs busy while it samples, so
+independent batches overlap; nothing is skipped, every step is the full chain on its own batch).
+`latency` is the same step on a single stream, eager launches.  `e2e` is the pipelined throughput
+through host pinned buffers with the H2D/D2H copies inside every step;
 `roofline` is for the dominant kernel (farthest point sampling, SA1); `cpu_baseline` is the CPU
 oracle (oracle/, a port of the reference kernels' semantics) on this box's host cores.
 
@@ -34,7 +38,7 @@ import numpy as np  # noqa: E402
 
 BATCH = 16
 N_POINTS = 16384
-POOL = 4  # distinct input batches rotated through the timed steps
+STREAMS = 12  # batches in flight (one CUDA stream + graph + input batch + workspace each)
 
 
 def _peaks():
@@ -46,36 +50,49 @@ def _peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons while the timed regions run (NVML, 5 ms period; nvidia-smi fallback)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.max_sm, self.mask, self._stop_evt = index, [], None, 0, threading.Event()
 
     def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop_evt.is_set():
+                self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                self._stop_evt.wait(0.005)
+        except Exception:
+            q = "clocks.sm,clocks.max.sm"
+            while not self._stop_evt.is_set():
+                try:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = [float(c) for c in out.strip().split(",")]
+                    self.sm.append(a)
+                    self.max_sm = b
+                except Exception:
+                    pass
+                self._stop_evt.wait(0.1)
 
     def summary(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = sorted(n for bit, n in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                "reasons": reasons, "samples": len(self.sm)}
 
 
-def make_host_batches(rank, pool=POOL, batch=BATCH):
+def make_host_batches(rank, pool=STREAMS, batch=BATCH):
     from pdm_ssd_b200 import synthetic
     rng = np.random.default_rng(77 + rank)
     out = []
@@ -139,7 +156,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=48)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -168,85 +185,98 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    host = make_host_batches(rank)
+    from pdm_ssd_b200.sa_chain import PipelinedSAChain
+    host = make_host_batches(rank, pool=STREAMS)
     dev_batches = []
     for frames, feat2 in host:
         pts = torch.from_numpy(frames).to(dev)
-        dev_batches.append((pts[..., :3].contiguous(), pts[..., 3:].transpose(1, 2).contiguous(),
-                            torch.from_numpy(feat2).to(dev)))
-    chain = SAChain(BATCH, N_POINTS, device=dev)
+        dev_batches.append((pts[..., :3].contiguous(), (pts[..., 3:].transpose(1, 2).contiguous(),
+                                                        torch.from_numpy(feat2).to(dev))))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
-        xyz, f1, f2 = dev_batches[i % POOL]
-        chain.run(xyz, (f1, f2))
+    def reduce_max(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    # ---- device-resident throughput -------------------------------------------------------
-    for i in range(args.warmup):
-        step(i)
+    # ---- device-resident throughput: STREAMS batches in flight, one CUDA graph per slot ----------
+    pipe = PipelinedSAChain(BATCH, STREAMS, N_POINTS, device=dev)
+    pipe.capture(dev_batches)
+
+    def pipelined(p, nsteps):
+        p.begin()
+        for i in range(nsteps):
+            p.submit()
+        p.end()
+
+    pipelined(pipe, max(args.warmup, STREAMS))
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # per-kernel timing of the dominant kernel (FPS of SA1) with events around its launch
-    fps_ev = []
-    orig_fps = chain.be.farthest_point_sampling_wrapper
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    pipelined(pipe, args.steps)
+    e1.record()
+    barrier()
+    ms_max = reduce_max(e0.elapsed_time(e1))
+    value = world * BATCH * args.steps / (ms_max * 1e-3)
+    launches = pipe.launches_per_step * args.steps   # our kernels inside the replayed graphs
 
-    class _Timed:  # thin proxy: times SA1's FPS launch on the launch stream, forwards everything else
+    # ---- latency: the same step on ONE stream, eager launches; times the dominant kernel ------------
+    chain = SAChain(BATCH, N_POINTS, device=dev)
+    fps_ev = []
+    orig_be = chain.be
+    orig_fps = orig_be.farthest_point_sampling_wrapper
+
+    class _Timed:  # thin proxy: CUDA events around SA1's FPS launch on the launch stream
         def __getattr__(self, name):
             return getattr(orig_be, name)
 
         def farthest_point_sampling_wrapper(self, b, n, m, *a):
             if n != N_POINTS:
                 return orig_fps(b, n, m, *a)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record()
             r = orig_fps(b, n, m, *a)
-            e1.record()
-            fps_ev.append((e0, e1))
+            x1.record()
+            fps_ev.append((x0, x1))
             return r
-    orig_be = chain.be
-    chain.be = _Timed()
-    _lib.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        step(i)
-    e1.record()
-    barrier()
-    launches = _lib.launch_count()
-    chain.be = orig_be
-    ms = e0.elapsed_time(e1)
-    fps_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in fps_ev]))
-    clocks = sampler.summary() if rank == 0 else None
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * BATCH * args.steps / (ms_max * 1e-3)
-
-    # ---- end to end: host pinned buffers in, host results out -----------------------------
-    hchain = HostSAChain(BATCH, N_POINTS, device=dev)
-    pinned = [(torch.from_numpy(f).pin_memory(), torch.from_numpy(g).pin_memory()) for f, g in host]
     for i in range(3):
-        hchain.run(*pinned[i % POOL])
+        chain.run(*dev_batches[i % STREAMS])
+    chain.be = _Timed()
+    l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    l0.record()
+    nlat = max(5, min(args.steps, 20))
+    for i in range(nlat):
+        chain.run(*dev_batches[i % STREAMS])
+    l1.record()
+    barrier()
+    chain.be = orig_be
+    latency_ms = reduce_max(l0.elapsed_time(l1)) / nlat
+    fps_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in fps_ev]))
+
+    # ---- end to end: host pinned buffers in, host results out, copies inside every step ---------------
+    hpipe = PipelinedSAChain(BATCH, STREAMS, N_POINTS, device=dev, host=True)
+    pinned = [(torch.from_numpy(f).pin_memory(), torch.from_numpy(g).pin_memory()) for f, g in host]
+    hpipe.capture(pinned)
+    pipelined(hpipe, STREAMS)
     barrier()
     h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h0.record()
-    for i in range(args.steps):
-        out = hchain.run(*pinned[i % POOL])
+    pipelined(hpipe, args.steps)
     h1.record()
     barrier()
-    checksum = int(out[1]["fps_idx"].sum().item())  # touches the host copy of the last result
-    t = torch.tensor([h0.elapsed_time(h1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * BATCH * args.steps / (float(t.item()) * 1e-3)
+    checksum = int(sum(int(c.h_out[1]["fps_idx"].sum().item()) for c in hpipe.chains))  # reads the host copies
+    e2e_value = world * BATCH * args.steps / (reduce_max(h0.elapsed_time(h1)) * 1e-3)
+    clocks = sampler.summary() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -271,15 +301,19 @@ def main():
         "config": {"workload": "configs[1]: pointnet2 SA op chain (FPS 16384->4096->1024, ball query r=0.8/1.6 x32, "
                                "xyz+feature grouping C=1/64), KITTI-shaped synthetic frames",
                    "batch_per_gpu": BATCH, "points_per_frame": N_POINTS,
-                   "l2": "step working set %.0f MB > 126 MB L2; %d distinct input batches rotated" % (ab["total"] * BATCH / 1e6, POOL)},
+                   "streams": STREAMS, "cuda_graphs": True,
+                   "l2": "step working set %.0f MB > 126 MB L2; %d distinct input batches (one per stream slot)" % (ab["total"] * BATCH / 1e6, STREAMS)},
         "roofline": {"kernel": "fps_bucket_kernel (SA1 farthest point sampling)", "bound": "hbm", "achieved": achieved,
                      "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": fps_bytes, "kernel_ms": fps_kernel_ms,
-                     "note": "latency-bound by design: 4095 dependent argmax rounds per frame; see rounds_per_s",
+                     "note": "kernel timed alone on one stream (latency pass); latency-bound by design: 4095 dependent "
+                             "argmax rounds per frame, one CTA per frame -> see rounds_per_s; throughput comes from overlapping batches",
                      "rounds_per_s": 4095.0 / (fps_kernel_ms * 1e-3)},
         "chain_hbm": {"algorithmic_bytes_per_frame": ab["total"], "achieved_gbs": chain_gbs, "frac": chain_gbs / peak},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": hchain.h2d_bytes,
-                "d2h_bytes_per_step": hchain.d2h_bytes, "checksum": checksum},
+        "latency": {"ms_per_step_single_stream": latency_ms, "frames_per_s_single_stream": world * BATCH / (latency_ms * 1e-3),
+                    "what": "same step, one stream, eager launches (no graphs, no overlap between batches)"},
+        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": hpipe.h2d_bytes,
+                "d2h_bytes_per_step": hpipe.d2h_bytes, "checksum": checksum, "streams": STREAMS},
         "gpu_launches": int(launches), "clocks": clocks,
     }
 
@@ -291,19 +325,19 @@ def main():
         if ref is not None:
             rchain = SAChain(BATCH, N_POINTS, device=dev, backend=ref)
             for i in range(2):
-                rchain.run(*[(b[0], (b[1], b[2])) for b in dev_batches][i % POOL])
+                rchain.run(*dev_batches[i % STREAMS])
             torch.cuda.synchronize()
             r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             nref = max(3, min(10, args.steps))
             r0.record()
             for i in range(nref):
-                b = dev_batches[i % POOL]
-                rchain.run(b[0], (b[1], b[2]))
+                rchain.run(*dev_batches[i % STREAMS])
             r1.record()
             torch.cuda.synchronize()
             rms = r0.elapsed_time(r1) / nref
             line["reference_cuda"] = {"value": BATCH / (rms * 1e-3), "unit": "frames/s", "ms_per_step": rms,
-                                      "what": "reference pointnet2_batch kernels recompiled for sm_100 (oracle/_ref), same chain, 1 GPU"}
+                                      "what": "reference pointnet2_batch kernels recompiled for sm_100 (oracle/_ref), same chain, 1 GPU; "
+                                              "they launch on the legacy default stream, so batches cannot overlap"}
     except Exception as ex:  # informational only
         line["reference_cuda"] = {"unavailable": str(ex)[:120]}
 

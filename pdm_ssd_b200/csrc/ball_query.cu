@@ -340,9 +340,11 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     count_launch();
     cudaError_t e1 = cudaGetLastError();
     if (e1 == cudaSuccess) {
-        if (smem > 48 * 1024)
-            e1 = cudaFuncSetAttribute(bq_query_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e1 == cudaSuccess) {
+        if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK) {
+            cudaFreeAsync(scratch, st);
+            return PDM_ERR_UNSUPPORTED;  // message already recorded; caller falls back to the tiled kernel
+        }
+        {
             dim3 grid((m + kQueryWarps - 1) / kQueryWarps, b);
             bq_query_kernel<<<grid, kQueryWarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
                                                                  grids, cend, sorted, idx);

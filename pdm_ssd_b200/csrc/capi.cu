@@ -2,6 +2,10 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace pdm {
@@ -15,6 +19,21 @@ int fail(int code, const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code == 0 ? PDM_ERR_INVALID_ARG : code;
+}
+
+int ensure_dynamic_smem(const void *func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail((int)e, "cudaGetDevice: %s", cudaGetErrorString(e));
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = done[{func, dev}];
+    if (bytes <= cur) return PDM_OK;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
+    cur = bytes;
+    return PDM_OK;
 }
 
 // cuda_utils.h:10-14 of the reference, evaluated the same way (double log ratio, truncation).

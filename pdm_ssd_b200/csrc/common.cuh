@@ -55,6 +55,10 @@ __device__ __forceinline__ void st_cs_f1(float *p, float v) {
     asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize, set once per (kernel, device) and only raised:
+// keeps driver calls out of the steady state (and out of CUDA-graph capture).
+int ensure_dynamic_smem(const void *func, size_t bytes);
+
 // reference host helper cuda_utils.h:10-14 (block size the reference FPS would use);
 // decides the tie-break order our FPS has to reproduce.
 int ref_fps_block_size(int n);

@@ -551,8 +551,7 @@ static int launch_bucket(int b, int n, int m, int p, const float *xyz, float *te
                          int *stats, cudaStream_t st) {
     using L = FpsSmem<NW, BPW, KMAX>;
     auto kern = fps_bucket_kernel<NW, BPW, KMAX>;
-    // per launch (a few hundred ns): the attribute is per device, and one process may drive several
-    PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+    if (int rc = ensure_dynamic_smem((const void *)kern, L::kBytes)) return rc;
     kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, stats, nullptr);
     count_launch();
     PDM_CHECK_LAUNCH("farthest_point_sampling(bucket)");
@@ -610,7 +609,7 @@ extern "C" int pdm_debug_fps_trace(int b, int n, int m, const float *xyz, float 
     while ((1 << p) < ref_fps_block_size(n)) ++p;
     using L = FpsSmem<16, 32, 8>;
     auto kern = fps_bucket_kernel<16, 32, 8, true>;
-    PDM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kBytes));
+    if (int rc = ensure_dynamic_smem((const void *)kern, L::kBytes)) return rc;
     kern<<<b, 512, L::kBytes, (cudaStream_t)stream>>>(n, m, p, xyz, temp, idx, stats, trace);
     PDM_CHECK_LAUNCH("debug_fps_trace");
     return PDM_OK;

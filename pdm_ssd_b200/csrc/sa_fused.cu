@@ -198,7 +198,7 @@ extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample
         return fail(PDM_ERR_INVALID_ARG, "sa_fused_forward: null pointer");
     if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "sa_fused_forward: batch > 65535");
     const size_t smem = sizeof(float) * ((size_t)2 * P.act_floats + P.w_floats + kSAMaxC);
-    PDM_CHECK_CUDA(cudaFuncSetAttribute(sa_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ensure_dynamic_smem((const void *)sa_fused_kernel, smem)) return rc;
     const int cpb = kSARows / nsample;
     dim3 grid((m + cpb - 1) / cpb, b);
     sa_fused_kernel<<<grid, kSAThreads, smem, (cudaStream_t)stream>>>(P, xyz, features, new_xyz, idx, packed, out);
