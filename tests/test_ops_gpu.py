@@ -244,3 +244,91 @@ def test_errors_raise_instead_of_exit():
     with pytest.raises(_lib.PdmOpsError):
         ours.farthest_point_sampling_wrapper(1, 0, 4, x[:, :0].contiguous(), torch.zeros((1, 0), device=DEV),
                                              torch.zeros((1, 4), dtype=torch.int32, device=DEV))
+
+
+# ------------------------------------------------------------------ streams, devices, big frames
+def test_ops_follow_the_current_stream():
+    """Launches go to torch's current stream (the reference uses the legacy default stream)."""
+    xyz = _t(synthetic.kitti_batch(2, 4096, first_frame=30)[..., :3].copy())
+    want = oracle.fps(xyz.cpu().numpy(), 512)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        big = torch.empty(64 << 20, device=DEV).normal_()       # keeps the side stream busy first
+        idx = pu.farthest_point_sample(xyz, 512)
+        new_xyz = pu.gather_operation(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+        bq = pu.ball_query(0.8, 16, xyz, new_xyz)
+    side.synchronize()
+    assert np.array_equal(idx.cpu().numpy(), want)
+    assert np.array_equal(bq.cpu().numpy(), oracle.ball_query(0.8, 16, xyz.cpu().numpy(), new_xyz.cpu().numpy()))
+    del big
+
+
+def test_cuda_graph_capture_of_the_chain():
+    """The whole chain (kernels, scratch cudaMallocAsync/FreeAsync) is capturable and replayable."""
+    from pdm_ssd_b200.sa_chain import SAChain, SALayerCfg
+    layers = (SALayerCfg(512, 0.8, 16, 1), SALayerCfg(128, 1.6, 16, 4))
+    fr = synthetic.kitti_batch(2, 2048, first_frame=40)
+    xyz = _t(fr[..., :3].copy())
+    f1 = _t(fr[..., 3:].transpose(0, 2, 1).copy())
+    f2 = torch.randn(2, 4, 512, device=DEV)
+    chain = SAChain(2, 2048, layers, DEV)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        chain.run(xyz, (f1, f2))
+    st.synchronize()
+    eager = [w["ball_idx"].clone() for w in chain.ws] + [chain.ws[1]["grouped_feat"].clone()]
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        chain.run(xyz, (f1, f2))
+    for w in chain.ws:
+        w["ball_idx"].fill_(-1)
+    chain.ws[1]["grouped_feat"].zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    got = [w["ball_idx"] for w in chain.ws] + [chain.ws[1]["grouped_feat"]]
+    for a, b in zip(eager, got):
+        assert torch.equal(a, b)
+
+
+def test_waymo_scale_frame():
+    """BASELINE configs[4] shape: 163840 points.  FPS takes the any-size kernel, ball query the grid."""
+    rng = np.random.default_rng(9)
+    xyz = (rng.uniform(0, 1, (1, 163840, 3)) * np.array([150.4, 150.4, 6.0]) - np.array([75.2, 75.2, 2.0])).astype(np.float32)
+    xyz[0, 100000:] = xyz[0, :63840]                       # heavy duplication -> ties
+    m = 1024
+    want, want_t = oracle.fps(xyz, m, return_temp=True)
+    got, got_t = our_fps(xyz, m, return_temp=True)
+    assert np.array_equal(got, want) and np.array_equal(got_t, want_t)
+    new_xyz = np.take_along_axis(xyz, want[..., None].astype(np.int64).repeat(3, -1), 1)
+    assert np.array_equal(our_bq(0.8, 32, xyz, new_xyz), oracle.ball_query(0.8, 32, xyz, new_xyz))
+    assert np.array_equal(our_bq(40.0, 64, xyz, new_xyz[:, :64]), oracle.ball_query(40.0, 64, xyz, new_xyz[:, :64]))
+
+
+def test_ball_query_degenerate_inputs():
+    rng = np.random.default_rng(4)
+    # all points identical; radius larger than the scene; radius tiny; nsample > n; non-finite coordinates
+    same = np.ones((1, 40, 3), np.float32)
+    assert np.array_equal(our_bq(0.1, 8, same, same[:, :3]), oracle.ball_query(0.1, 8, same, same[:, :3]))
+    pts = rng.uniform(-1, 1, (2, 300, 3)).astype(np.float32)
+    q = pts[:, :17].copy()
+    for r, s in ((1000.0, 16), (1e-6, 4), (0.5, 400)):
+        assert np.array_equal(our_bq(r, s, pts, q), oracle.ball_query(r, s, pts, q))
+    bad = pts.copy()
+    bad[0, 5] = np.nan
+    bad[1, 7, 0] = np.inf
+    assert np.array_equal(our_bq(0.5, 16, bad, q), oracle.ball_query(0.5, 16, bad, q))
+
+
+def test_empty_and_trivial_sizes():
+    z = torch.zeros((0, 8, 3), device=DEV)
+    ours.farthest_point_sampling_wrapper(0, 8, 4, z, torch.zeros((0, 8), device=DEV), torch.zeros((0, 4), dtype=torch.int32, device=DEV))
+    x = torch.rand((2, 50, 3), device=DEV)
+    idx = torch.full((2, 0), 7, dtype=torch.int32, device=DEV)
+    ours.farthest_point_sampling_wrapper(2, 50, 0, x, torch.full((2, 50), 1e10, device=DEV), idx)   # m = 0: no-op
+    one = our_fps(x.cpu().numpy(), 1)
+    assert (one == 0).all()
+    out = torch.empty((2, 3, 0), device=DEV)
+    ours.gather_points_wrapper(2, 3, 50, 0, x.transpose(1, 2).contiguous(), torch.zeros((2, 0), dtype=torch.int32, device=DEV), out)
+    bq = torch.zeros((2, 0, 4), dtype=torch.int32, device=DEV)
+    ours.ball_query_wrapper(2, 50, 0, 0.5, 4, torch.zeros((2, 0, 3), device=DEV), x, bq)
