@@ -189,37 +189,76 @@ pdm_bev_kernel(int c_total, int K, NeckCfg cfg, const float *__restrict__ feats,
             for (int i = 0; i < kCPL; ++i) acc[i] = 0.f;
             if (cx < X) {
                 const int cell0 = (cx * Y + cy) * Z;  // frame-local index of the pillar's z = 0 cell
+                // the pillar's Z cell ends are contiguous: fetched 32 at a time by the lanes in one
+                // coalesced load (a serial walk is Z dependent L2 round trips even for empty pillars)
                 int s = cell0 == 0 ? 0 : __ldg(ce + cell0 - 1);
-                for (int z = 0; z < Z; ++z) {
-                    const int e_end = __ldg(ce + cell0 + z);
+                for (int zb = 0; zb < Z; zb += 32) {
+                  const int zn = min(32, Z - zb);
+                  const int ends = lane < zn ? __ldg(ce + cell0 + zb + lane) : 0;
+                  const int last_end = __shfl_sync(0xffffffffu, ends, zn - 1);
+                  if (last_end == s) continue;          // nothing in these cells (most pillars)
+                  for (int zi = 0; zi < zn; ++zi) {
+                    const int e_end = __shfl_sync(0xffffffffu, ends, zi);
                     if (e_end > s) {  // warp-uniform
                         float num[kCPL];
 #pragma unroll
                         for (int i = 0; i < kCPL; ++i) num[i] = 0.f;
                         float den = 0.f;
-                        unsigned last = 0u;  // entry ids are visited in ascending order: next = min id > last
-                        bool first = true;
-                        for (int it = s; it < e_end; ++it) {
-                            unsigned cand = 0xffffffffu;
-                            for (int q = s + lane; q < e_end; q += 32) {
-                                const unsigned id = (unsigned)__ldg(srt + q);
-                                if ((first || id > last) && id < cand) cand = id;
-                            }
-                            const unsigned id = __reduce_min_sync(0xffffffffu, cand);
-                            last = id;
-                            first = false;
-                            const float wv = __ldg(wts + id);
-                            const float *f = feats + (size_t)(id / (unsigned)K) * c_total + cb + lane;
+                        const int cnt = e_end - s;
+                        if (cnt <= 32) {
+                            // usual case: one entry per lane; a bitonic network over the warp puts the
+                            // entry ids in ascending order (padding = 0xffffffff sorts last), then the
+                            // weights and row indices are fetched by all lanes at once and the rows
+                            // are streamed in order (their addresses are known up front, so the loads
+                            // of consecutive entries overlap; only the fp32 adds are serial).
+                            unsigned v = lane < cnt ? (unsigned)__ldg(srt + s + lane) : 0xffffffffu;
 #pragma unroll
-                            for (int i = 0; i < kCPL; ++i)
-                                if (cb + lane + 32 * i < c_total) num[i] = __fadd_rn(num[i], __fmul_rn(wv, __ldg(f + 32 * i)));
-                            den = __fadd_rn(den, fabsf(wv));
+                            for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+                                for (int j = k >> 1; j > 0; j >>= 1) {
+                                    const unsigned o = __shfl_xor_sync(0xffffffffu, v, j);
+                                    const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+                                    v = keep_min ? min(v, o) : max(v, o);
+                                }
+                            }
+                            const float wq = lane < cnt ? __ldg(wts + v) : 0.f;
+                            const unsigned pq = lane < cnt ? v / (unsigned)K : 0u;
+#pragma unroll 2
+                            for (int it = 0; it < cnt; ++it) {
+                                const float wv = __shfl_sync(0xffffffffu, wq, it);
+                                const float *f = feats + (size_t)__shfl_sync(0xffffffffu, pq, it) * c_total + cb + lane;
+#pragma unroll
+                                for (int i = 0; i < kCPL; ++i)
+                                    if (cb + lane + 32 * i < c_total) num[i] = __fadd_rn(num[i], __fmul_rn(wv, __ldg(f + 32 * i)));
+                                den = __fadd_rn(den, fabsf(wv));
+                            }
+                        } else {
+                            // crowded cell: repeated min-selection over the unsorted list
+                            unsigned last = 0u;
+                            bool first = true;
+                            for (int it = s; it < e_end; ++it) {
+                                unsigned cand = 0xffffffffu;
+                                for (int q = s + lane; q < e_end; q += 32) {
+                                    const unsigned id = (unsigned)__ldg(srt + q);
+                                    if ((first || id > last) && id < cand) cand = id;
+                                }
+                                const unsigned id = __reduce_min_sync(0xffffffffu, cand);
+                                last = id;
+                                first = false;
+                                const float wv = __ldg(wts + id);
+                                const float *f = feats + (size_t)(id / (unsigned)K) * c_total + cb + lane;
+#pragma unroll
+                                for (int i = 0; i < kCPL; ++i)
+                                    if (cb + lane + 32 * i < c_total) num[i] = __fadd_rn(num[i], __fmul_rn(wv, __ldg(f + 32 * i)));
+                                den = __fadd_rn(den, fabsf(wv));
+                            }
                         }
                         const float dn = __fadd_rn(den, cfg.eps);
 #pragma unroll
                         for (int i = 0; i < kCPL; ++i) acc[i] = __fadd_rn(acc[i], __fdiv_rn(num[i], dn));
                     }
                     s = e_end;
+                  }
                 }
             }
 #pragma unroll

@@ -86,3 +86,17 @@ def test_neck_plugin_module_contract():
     coef = torch.nn.functional.linear(feats, neck.coef.weight.cpu(), neck.coef.bias.cpu())
     want = O.neck_forward(coords, feats, coef.detach(), 2, RANGE, [0.4, 0.4, 0.4])
     assert _rel(out["spatial_features"].cpu(), want) < 1e-3
+
+
+def test_neck_crowded_cells_take_the_selection_path():
+    """> 32 entries in one cell (many centres inside one voxel) exercises the min-selection branch."""
+    rng = np.random.default_rng(3)
+    m = 200
+    xyz = np.array([10.2, 0.2, -1.0], np.float32) + rng.uniform(-0.15, 0.15, (m, 3)).astype(np.float32)
+    coords = torch.from_numpy(np.concatenate([np.zeros((m, 1), np.float32), xyz], 1))
+    feats = torch.randn(m, 16, generator=torch.Generator().manual_seed(2))
+    coef = torch.randn(m, 9, generator=torch.Generator().manual_seed(3))
+    voxel = [0.4, 0.4, 0.4]
+    want = O.neck_forward(coords, feats, coef, 1, RANGE, voxel)
+    got = pdm_neck.neck_forward(coords.to(DEV), feats.to(DEV), coef.to(DEV), 1, RANGE, voxel, O.grid_size(RANGE, voxel))
+    assert _rel(got.cpu(), want) < 1e-3
