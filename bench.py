@@ -221,11 +221,17 @@ def main():
         sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    tw0 = time.perf_counter()
     e0.record()
     pipelined(pipe, args.steps)
     e1.record()
+    tw1 = time.perf_counter()
     barrier()
-    ms_max = reduce_max(e0.elapsed_time(e1))
+    ms_rank = e0.elapsed_time(e1)
+    if os.environ.get("PDM_BENCH_DEBUG"):
+        print("rank %d: pipelined %.3f ms (events) for %d steps; submit loop %.3f ms wall; total %.3f ms wall"
+              % (rank, ms_rank, args.steps, (tw1 - tw0) * 1e3, (time.perf_counter() - tw0) * 1e3), file=sys.stderr, flush=True)
+    ms_max = reduce_max(ms_rank)
     value = world * BATCH * args.steps / (ms_max * 1e-3)
     launches = pipe.launches_per_step * args.steps   # our kernels inside the replayed graphs
 

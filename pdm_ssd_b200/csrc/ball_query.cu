@@ -329,8 +329,8 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     const size_t sz_cid = (((size_t)b * n * sizeof(int) + 255) / 256) * 256;
     const size_t sz_cend = (size_t)b * cmax * sizeof(int);
     const size_t sz_sorted = (size_t)b * n * sizeof(float4);
-    char *scratch = nullptr;
-    PDM_CHECK_CUDA(cudaMallocAsync((void **)&scratch, sz_grid + sz_cid + sz_cend + sz_sorted, st));
+    char *scratch = static_cast<char *>(stream_scratch(st, sz_grid + sz_cid + sz_cend + sz_sorted));
+    if (!scratch) return PDM_ERR_INVALID_ARG;  // message recorded by stream_scratch
     BQGrid *grids = reinterpret_cast<BQGrid *>(scratch);
     int *cid = reinterpret_cast<int *>(scratch + sz_grid);
     int *cend = reinterpret_cast<int *>(scratch + sz_grid + sz_cid);
@@ -340,10 +340,8 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     count_launch();
     cudaError_t e1 = cudaGetLastError();
     if (e1 == cudaSuccess) {
-        if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK) {
-            cudaFreeAsync(scratch, st);
+        if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK)
             return PDM_ERR_UNSUPPORTED;  // message already recorded; caller falls back to the tiled kernel
-        }
         {
             dim3 grid((m + kQueryWarps - 1) / kQueryWarps, b);
             bq_query_kernel<<<grid, kQueryWarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
@@ -352,7 +350,6 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
             e1 = cudaGetLastError();
         }
     }
-    cudaFreeAsync(scratch, st);
     if (e1 != cudaSuccess) return fail((int)e1, "ball_query(grid): %s", cudaGetErrorString(e1));
     return PDM_OK;
 }

@@ -36,6 +36,30 @@ int ensure_dynamic_smem(const void *func, size_t bytes) {
     return PDM_OK;
 }
 
+void *stream_scratch(cudaStream_t st, size_t bytes) {
+    struct Buf { void *ptr = nullptr; size_t size = 0; };
+    static std::mutex mu;
+    static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { fail(PDM_ERR_INVALID_ARG, "stream_scratch: cudaGetDevice failed"); return nullptr; }
+    std::lock_guard<std::mutex> lock(mu);
+    Buf &b = bufs[{dev, st}];
+    if (bytes <= b.size) return b.ptr;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) {
+        fail(PDM_ERR_UNSUPPORTED, "scratch would grow to %zu B during stream capture: run the call once before capturing", bytes);
+        return nullptr;
+    }
+    const size_t want = bytes + bytes / 4;   // head-room so that slightly larger calls do not reallocate
+    void *p = nullptr;
+    const cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { fail((int)e, "stream_scratch: cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); return nullptr; }
+    b.ptr = p;      // the outgrown buffer stays allocated: earlier work / captured graphs may still use it
+    b.size = want;
+    return p;
+}
+
 // cuda_utils.h:10-14 of the reference, evaluated the same way (double log ratio, truncation).
 int ref_fps_block_size(int n) {
     const int pow_2 = (int)(log((double)n) / log(2.0));

@@ -59,6 +59,15 @@ __device__ __forceinline__ void st_cs_f1(float *p, float v) {
 // keeps driver calls out of the steady state (and out of CUDA-graph capture).
 int ensure_dynamic_smem(const void *func, size_t bytes);
 
+// Persistent scratch, one buffer per (device, stream), grown on demand and never moved while in
+// use: work on one stream is serialised, so consecutive calls can share it, and a CUDA graph that
+// captured a call keeps a valid address (buffers that were outgrown are retired, not freed).
+// Stream-ordered cudaMallocAsync inside a captured step turned every graph launch into ~1 ms of
+// driver work once four processes drove four GPUs; a plain pointer costs nothing.
+// Returns nullptr and records an error if the buffer would have to grow during stream capture
+// (run the call once eagerly first).
+void *stream_scratch(cudaStream_t st, size_t bytes);
+
 // reference host helper cuda_utils.h:10-14 (block size the reference FPS would use);
 // decides the tie-break order our FPS has to reproduce.
 int ref_fps_block_size(int n);

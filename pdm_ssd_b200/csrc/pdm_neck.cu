@@ -316,8 +316,8 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
     const size_t sz_count = align((size_t)cells_per_frame * batch * 4);
     const int chunks_per_frame = (int)((cells_per_frame + kScanChunk - 1) / kScanChunk);
     const size_t sz_tot = align((size_t)batch * 4) + align((size_t)batch * chunks_per_frame * 4);
-    char *ws = nullptr;
-    PDM_CHECK_CUDA(cudaMallocAsync((void **)&ws, sz_keys + sz_w + sz_sorted + sz_count + sz_tot, st));
+    char *ws = static_cast<char *>(stream_scratch(st, sz_keys + sz_w + sz_sorted + sz_count + sz_tot));
+    if (!ws) return PDM_ERR_INVALID_ARG;  // message recorded by stream_scratch
     int *keys = dbg_keys ? dbg_keys : reinterpret_cast<int *>(ws);
     float *wts = dbg_w ? dbg_w : reinterpret_cast<float *>(ws + sz_keys);
     int *sorted = reinterpret_cast<int *>(ws + sz_keys + sz_w);
@@ -350,7 +350,6 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
         count_launch();
         err = cudaGetLastError();
     }
-    cudaFreeAsync(ws, st);
     if (err != cudaSuccess) return fail((int)err, "neck_forward: %s", cudaGetErrorString(err));
     return PDM_OK;
 }

@@ -54,11 +54,14 @@ def test_neck_matches_oracle(batch, m, c, degree, dil, oor):
     want_keys = torch.where(dbg["valid"], dbg["key3"], torch.full_like(dbg["key3"], -1)).int()
     assert torch.equal(keys.cpu(), want_keys), "dilation-grid keys must be bit-exact"
     wv = dbg["w"][dbg["valid"]]
-    assert _rel(wts.cpu()[dbg["valid"]], wv) < 1e-5
+    werr = _rel(wts.cpu()[dbg["valid"]], wv)
+    assert werr < 1e-5, "entry weights differ: %g" % werr
     assert got.shape == want.shape
-    assert _rel(got.cpu(), want) < 1e-3
+    ferr = _rel(got.cpu(), want)
+    assert ferr < 1e-3, "BEV features differ: %g" % ferr
     # empty pillars are exactly zero and occupancy matches
-    assert torch.equal((got.cpu().abs().sum(1) > 0), (want.abs().sum(1) > 0))
+    occ_got, occ_want = (got.cpu() != 0).any(1), (want != 0).any(1)
+    assert torch.equal(occ_got, occ_want), "occupancy differs in %d pillars" % int((occ_got != occ_want).sum())
 
 
 def test_neck_is_deterministic():
