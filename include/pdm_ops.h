@@ -90,6 +90,14 @@ int pdm_three_interpolate(int b, int c, int m, int n, const float *points, const
 int pdm_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                const float *weight, float *grad_points, void *stream);
 
+/* QueryAndGroup.forward after the ball query in one pass (pointnet2_utils.py:250-257: xyz^T copy,
+ * group xyz, subtract centres, group features, cat).  xyz (B,N,3), new_xyz (B,npoints,3),
+ * features (B,C,N) or NULL when c == 0, idx (B,npoints,nsample) ->
+ * out (B, 3*use_xyz + C, npoints, nsample) with channel order [xyz - centre, features]. */
+int pdm_query_and_group(int b, int c, int n, int npoints, int nsample, int use_xyz, const float *xyz,
+                        const float *new_xyz, const float *features, const int *idx, float *out,
+                        void *stream);
+
 /* ---- fused set-abstraction scale ---------------------------------------------------------- */
 
 /* One scale of _PointnetSAModuleBase.forward in a single kernel (inference): replaces

@@ -78,6 +78,44 @@ scatter_add_kernel(int c, int n, size_t cols, const float *__restrict__ grad_out
               __ldg(grad_out + ((size_t)bi * c + ci) * cols + j));
 }
 
+// QueryAndGroup.forward after the ball query, in one pass (pointnet2_utils.py:250-257):
+//   out[b, 0:3, p, s]   = xyz[b, idx[b,p,s], :] - new_xyz[b, p, :]
+//   out[b, 3+c, p, s]   = features[b, c, idx[b,p,s]]
+// The reference materialises xyz^T, groups it, subtracts the centres in place, groups the features
+// and concatenates: five full passes over (B, C, npoint, nsample) tensors.  Here the concatenated
+// tensor is written once.  grid.y = 0 handles the three xyz channels, grid.y >= 1 feature chunks.
+template <int CH>
+__global__ void __launch_bounds__(256)
+query_group_kernel(int c, int n, int npoints, int nsample, int use_xyz, const float *__restrict__ xyz,
+                   const float *__restrict__ new_xyz, const float *__restrict__ feats,
+                   const int *__restrict__ idx, float *__restrict__ out) {
+    const size_t cols = (size_t)npoints * nsample;
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    const int bi = blockIdx.z;
+    const int ctot = (use_xyz ? 3 : 0) + c;
+    const int id = __ldg(idx + (size_t)bi * cols + j);
+    float *dst = out + (size_t)bi * ctot * cols + j;
+    if (use_xyz && blockIdx.y == 0) {
+        const int p = (int)(j / nsample);
+        const float *pp = xyz + ((size_t)bi * n + id) * 3;
+        const float *qq = new_xyz + ((size_t)bi * npoints + p) * 3;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) st_cs_f1(dst + (size_t)a * cols, __fsub_rn(__ldg(pp + a), __ldg(qq + a)));
+        return;
+    }
+    const int c0 = ((int)blockIdx.y - (use_xyz ? 1 : 0)) * CH;
+    const float *src = feats + ((size_t)bi * c + c0) * n + id;
+    dst += (size_t)((use_xyz ? 3 : 0) + c0) * cols;
+    float v[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+        if (c0 + k < c) v[k] = __ldg(src + (size_t)k * n);
+#pragma unroll
+    for (int k = 0; k < CH; ++k)
+        if (c0 + k < c) st_cs_f1(dst + (size_t)k * cols, v[k]);
+}
+
 static int launch_group(int b, int c, int n, size_t cols, const float *points, const int *idx,
                         float *out, cudaStream_t st, const char *what) {
     if (b < 0 || c < 0 || n < 0) return fail(PDM_ERR_INVALID_ARG, "%s: negative size", what);
@@ -137,6 +175,28 @@ int pdm_group_points(int b, int c, int n, int npoints, int nsample, const float 
     if (npoints < 0 || nsample < 0) return pdm::fail(PDM_ERR_INVALID_ARG, "group_points: negative size");
     return pdm::launch_group(b, c, n, (size_t)npoints * nsample, points, idx, out,
                              (cudaStream_t)stream, "group_points");
+}
+
+int pdm_query_and_group(int b, int c, int n, int npoints, int nsample, int use_xyz, const float *xyz,
+                        const float *new_xyz, const float *features, const int *idx, float *out,
+                        void *stream) {
+    using namespace pdm;
+    if (b < 0 || c < 0 || n < 0 || npoints < 0 || nsample < 0)
+        return fail(PDM_ERR_INVALID_ARG, "query_and_group: negative size");
+    if (!use_xyz && c == 0) return fail(PDM_ERR_INVALID_ARG, "query_and_group: no xyz and no features");
+    if (b == 0 || npoints == 0 || nsample == 0) return PDM_OK;
+    if (!idx || !out || (use_xyz && (!xyz || !new_xyz)) || (c > 0 && !features))
+        return fail(PDM_ERR_INVALID_ARG, "query_and_group: null pointer");
+    constexpr int CH = 8;
+    const int chunks = (c + CH - 1) / CH + (use_xyz ? 1 : 0);
+    if (b > 65535 || chunks > 65535) return fail(PDM_ERR_UNSUPPORTED, "query_and_group: b/c too large");
+    const size_t cols = (size_t)npoints * nsample;
+    dim3 grid((unsigned)((cols + 255) / 256), chunks, b);
+    query_group_kernel<CH><<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, npoints, nsample, use_xyz ? 1 : 0, xyz,
+                                                                  new_xyz, features, idx, out);
+    count_launch();
+    PDM_CHECK_LAUNCH("query_and_group");
+    return PDM_OK;
 }
 
 int pdm_gather_points_grad(int b, int c, int n, int npoints, const float *grad_out, const int *idx,

@@ -199,6 +199,9 @@ class QueryAndGroup(nn.Module):
 
     def forward(self, xyz: torch.Tensor, new_xyz: torch.Tensor, features: torch.Tensor = None) -> torch.Tensor:
         idx = ball_query(self.radius, self.nsample, xyz, new_xyz)
+        if (_backend is _native and not torch.is_grad_enabled() and xyz.is_cuda
+                and (features is not None or self.use_xyz)):
+            return _query_and_group_fused(xyz, new_xyz, features, idx, self.use_xyz)
         channels_first_xyz = xyz.transpose(1, 2).contiguous()
         local_xyz = grouping_operation(channels_first_xyz, idx)
         local_xyz -= new_xyz.transpose(1, 2).unsqueeze(-1)
@@ -207,6 +210,24 @@ class QueryAndGroup(nn.Module):
             return local_xyz
         grouped = grouping_operation(features, idx)
         return torch.cat([local_xyz, grouped], dim=1) if self.use_xyz else grouped
+
+
+def _query_and_group_fused(xyz, new_xyz, features, idx, use_xyz):
+    """One kernel for group-xyz / subtract-centre / group-features / cat (inference, native backend).
+    Bit-identical to the unfused sequence: the same gathers and the same fp32 subtraction."""
+    from . import _lib
+    B, N, _ = xyz.shape
+    _, M, S = idx.shape
+    C = 0 if features is None else features.shape[1]
+    feats = features.contiguous() if features is not None else None
+    out = torch.empty((B, (3 if use_xyz else 0) + C, M, S), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = _lib.load().pdm_query_and_group(
+            B, C, N, M, S, 1 if use_xyz else 0, xyz.contiguous().data_ptr(), new_xyz.contiguous().data_ptr(),
+            feats.data_ptr() if feats is not None else None, idx.data_ptr(), out.data_ptr(),
+            torch.cuda.current_stream(xyz.device).cuda_stream)
+    _lib.check(rc, "pdm_query_and_group")
+    return out
 
 
 class GroupAll(nn.Module):

@@ -332,3 +332,21 @@ def test_empty_and_trivial_sizes():
     ours.gather_points_wrapper(2, 3, 50, 0, x.transpose(1, 2).contiguous(), torch.zeros((2, 0), dtype=torch.int32, device=DEV), out)
     bq = torch.zeros((2, 0, 4), dtype=torch.int32, device=DEV)
     ours.ball_query_wrapper(2, 50, 0, 0.5, 4, torch.zeros((2, 0, 3), device=DEV), x, bq)
+
+
+@pytest.mark.parametrize("C,use_xyz", [(0, True), (1, True), (64, True), (17, False)])
+def test_query_and_group_fused_is_bit_identical(C, use_xyz, ref_ext):
+    """a5: one-pass QueryAndGroup against the reference-shaped op sequence (and the reference kernels)."""
+    fr = _t(synthetic.kitti_batch(2, 4096, first_frame=12)[..., :3].copy())
+    feats = torch.randn(2, C, 4096, device=DEV) if C else None
+    with torch.no_grad():
+        fi = pu.farthest_point_sample(fr, 512)
+        new_xyz = pu.gather_operation(fr.transpose(1, 2).contiguous(), fi).transpose(1, 2).contiguous()
+        fused = pu.QueryAndGroup(1.2, 16, use_xyz=use_xyz)(fr, new_xyz, feats)
+    with torch.enable_grad():                      # autograd on -> reference-shaped sequence over our kernels
+        plain = pu.QueryAndGroup(1.2, 16, use_xyz=use_xyz)(fr, new_xyz, feats)
+    assert fused.shape == plain.shape == (2, (3 if use_xyz else 0) + C, 512, 16)
+    assert torch.equal(fused, plain)
+    if ref_ext is not None:
+        with pu.use_backend(ref_ext), torch.no_grad():
+            assert torch.equal(pu.QueryAndGroup(1.2, 16, use_xyz=use_xyz)(fr, new_xyz, feats), fused)
