@@ -3,17 +3,20 @@
     SA1: FPS 16384 -> 4096, gather centres, ball query r=0.8 / 32, group xyz, group features (C=1)
     SA2: FPS  4096 -> 1024, gather centres, ball query r=1.6 / 32, group xyz, group features (C=64)
 
-It issues exactly the operator calls `_PointnetSAModuleBase.forward` + `QueryAndGroup.forward`
-make in the reference (pointnet2_modules.py:19-55, pointnet2_utils.py:241-264) -- through the
-nine-function backend API, so the same object drives our kernels or the reference extension --
-with all outputs pre-allocated (steady-state serving: no allocator traffic inside a step).
+It produces what `_PointnetSAModuleBase.forward` computes up to the shared MLP in the reference
+(pointnet2_modules.py:19-55): new_xyz and the QueryAndGroup tensor (B, 3+C, npoint, nsample) of
+each layer.  With the reference extension as backend it issues exactly the reference's operator
+sequence (pointnet2_utils.py:241-264: ball query, xyz^T, group, subtract, group, cat) through the
+nine-function API; with our backend the grouping half is the one-pass `pdm_query_and_group`
+(bit-identical output).  Outputs are pre-allocated (steady-state serving: no allocator traffic
+inside a step with our backend).
 """
 from dataclasses import dataclass
 from typing import Dict, Optional
 
 import torch
 
-from . import pointnet2_batch_cuda as _ours
+from . import _lib, pointnet2_batch_cuda as _ours
 
 
 @dataclass
@@ -55,12 +58,14 @@ class SAChain:
             m, s, c = L.npoint, L.nsample, L.channels
             f32 = dict(dtype=torch.float32, device=self.dev)
             i32 = dict(dtype=torch.int32, device=self.dev)
+            grouped = torch.empty((batch, 3 + c, m, s), **f32)   # QueryAndGroup output: [xyz - centre, features]
             self.ws.append(dict(
                 temp=torch.empty((batch, n), **f32), fps_idx=torch.empty((batch, m), **i32),
                 xyz_t=torch.empty((batch, 3, n), **f32), new_t=torch.empty((batch, 3, m), **f32),
                 new_xyz=torch.empty((batch, m, 3), **f32), ball_idx=torch.empty((batch, m, s), **i32),
-                grouped_xyz=torch.empty((batch, 3, m, s), **f32), grouped_feat=torch.empty((batch, c, m, s), **f32)))
+                grouped=grouped, grouped_xyz=grouped[:, :3], grouped_feat=grouped[:, 3:]))
             n = m
+        self.fused_group = self.be is _ours   # one-pass QueryAndGroup (pdm_query_and_group)
 
     def run(self, xyz: torch.Tensor, feats) -> Dict[str, torch.Tensor]:
         """xyz (B,N,3) device tensor; feats[i] (B,C_i,N_i) device tensor per layer.
@@ -76,9 +81,18 @@ class SAChain:
             ws["new_xyz"].copy_(ws["new_t"].transpose(1, 2))            # pointnet2_modules.py:32-35
             ws["ball_idx"].zero_()                                      # pointnet2_utils.py:218
             be.ball_query_wrapper(B, n, m, L.radius, s, ws["new_xyz"], cur, ws["ball_idx"])
-            be.group_points_wrapper(B, 3, n, m, s, ws["xyz_t"], ws["ball_idx"], ws["grouped_xyz"])
-            ws["grouped_xyz"].sub_(ws["new_t"].unsqueeze(-1))           # pointnet2_utils.py:252
-            be.group_points_wrapper(B, c, n, m, s, feat, ws["ball_idx"], ws["grouped_feat"])
+            if self.fused_group:
+                _lib.check(_lib.load().pdm_query_and_group(
+                    B, c, n, m, s, 1, cur.data_ptr(), ws["new_xyz"].data_ptr(), feat.data_ptr(),
+                    ws["ball_idx"].data_ptr(), ws["grouped"].data_ptr(),
+                    torch.cuda.current_stream(self.dev).cuda_stream), "pdm_query_and_group")
+            else:                                                       # the reference's sequence
+                gx = torch.empty((B, 3, m, s), dtype=torch.float32, device=self.dev)
+                be.group_points_wrapper(B, 3, n, m, s, ws["xyz_t"], ws["ball_idx"], gx)
+                gx.sub_(ws["new_t"].unsqueeze(-1))                      # pointnet2_utils.py:252
+                gf = torch.empty((B, c, m, s), dtype=torch.float32, device=self.dev)
+                be.group_points_wrapper(B, c, n, m, s, feat, ws["ball_idx"], gf)
+                torch.cat([gx, gf], dim=1, out=ws["grouped"])          # pointnet2_utils.py:257
             cur, n = ws["new_xyz"], m
         return self.ws
 
