@@ -183,6 +183,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("PDM_NCCL_DEBUG", "WARN")  # keep NCCL's banner off stdout: one JSON line only
         dist.init_process_group("nccl", device_id=dev)
 
     from pdm_ssd_b200.sa_chain import PipelinedSAChain
