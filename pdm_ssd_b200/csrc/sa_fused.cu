@@ -19,6 +19,8 @@
 // Thread tile: 8 rows x 4 output channels, activations stored channel-major A[c][row] so that a
 // thread's 8 rows are two 16-byte shared loads and its 4 weights one 16-byte (broadcast) load per
 // k: 32 FMAs per 3 LDS.128.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pdm {
@@ -160,6 +162,209 @@ sa_fused_kernel(SAFusedParams P, const float *__restrict__ xyz, const float *__r
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant (tcgen05 + TMEM).  Same data flow, but every layer
+//     D[128 rows x N] = A[128 x K] * W[N x K]^T
+// is issued by ONE thread as tcgen05.mma.kind::tf32 instructions (M = 128, K = 8 per instruction)
+// with the accumulator in tensor memory.  To stay at fp32 accuracy (budget 1e-3; plain TF32 would
+// sit right at it after three layers) each operand is split into a tf32-exact high part and a
+// remainder, and the product is formed as  hi*hi + lo*hi + hi*lo  (3 MMAs per k-step; measured
+// 1.1e-6 relative against fp64 in tools/micro/tc_gemm_test.cu).
+// Operands live in shared memory in the K-major, no-swizzle core-matrix layout
+//     smem[k/4][row][4 floats]      (8 rows x 16 bytes = one 128-byte core matrix;
+//                                    LBO = rows*16 between the two 16-byte K chunks of an MMA,
+//                                    SBO = 128 between 8-row groups)
+// which is exactly what a thread-per-row epilogue writes with conflict-free 16-byte stores, so the
+// activations never leave the SM between layers: TMEM -> registers (tcgen05.ld, one row per
+// thread) -> bias + ReLU -> hi/lo split -> shared memory -> next layer's MMA.
+// The max-pool uses redux.sync on the bit patterns (values are >= 0 after ReLU).
+// Every mbarrier wait is bounded: a wrong descriptor can produce wrong numbers, never a hang.
+constexpr int kTCThreads = 256;
+
+struct SATCParams {
+    int n, m, c_feat, nsample, use_xyz, n_layers;
+    int width[kSAMaxLayers + 1];
+    int kpad[kSAMaxLayers];        // input width of layer l rounded up to 8
+    int npad[kSAMaxLayers];        // output width rounded up to 16
+    int wpad4[kSAMaxLayers + 1];   // packed-buffer padding (multiple of 4), as in SAFusedParams
+    int woff[kSAMaxLayers], boff[kSAMaxLayers];
+    int a_floats;                  // floats of ONE of A_hi / A_lo
+    int w_floats;                  // floats of ONE of W_hi / W_lo
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
+    hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);   // what the tensor core reads of v
+    lo = v - hi;                                              // exact in fp32
+}
+
+__global__ void __launch_bounds__(kTCThreads, 1)
+sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__restrict__ feats,
+                   const float *__restrict__ new_xyz, const int *__restrict__ idx,
+                   const float *__restrict__ packed, float *__restrict__ out, int *__restrict__ err) {
+    extern __shared__ __align__(128) float smem[];
+    float *a_hi = smem;
+    float *a_lo = a_hi + P.a_floats;
+    float *w_hi = a_lo + P.a_floats;
+    float *w_lo = w_hi + P.w_floats;
+    float *bsm = w_lo + P.w_floats;                           // [128] bias of the current layer
+    unsigned *cmax = reinterpret_cast<unsigned *>(bsm + kSAMaxC);   // [centres per CTA][128] max-pool accumulators
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int bi = blockIdx.y;
+    const int S = P.nsample;
+    const int cpb = kSARows / S;
+    const int m0 = blockIdx.x * cpb;
+
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "r"(128));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    for (int t = tid; t < cpb * kSAMaxC; t += kTCThreads) cmax[t] = 0u;
+
+    // ---- gather the (xyz - centre, features) rows, split, store in the MMA layout -------------
+    {
+        const int r = tid & (kSARows - 1);
+        const int half = tid >> 7;
+        const int i = r / S, sidx = r - i * S;
+        const int mc = min(m0 + i, P.m - 1);
+        const int id = __ldg(idx + ((size_t)bi * P.m + mc) * S + sidx);
+        auto put = [&](int k, float v) {
+            float h, l;
+            split_tf32(v, h, l);
+            const int off = ((k >> 2) * kSARows + r) * 4 + (k & 3);
+            a_hi[off] = h;
+            a_lo[off] = l;
+        };
+        int c0 = 0;
+        if (P.use_xyz) {
+            if (half == 0) {
+                const float *pp = xyz + ((size_t)bi * P.n + id) * 3;
+                const float *qq = new_xyz + ((size_t)bi * P.m + mc) * 3;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) put(a, __fsub_rn(__ldg(pp + a), __ldg(qq + a)));
+            }
+            c0 = 3;
+        }
+        const float *f = feats + (size_t)bi * P.c_feat * P.n + id;
+        for (int c = half; c < P.c_feat; c += 2) put(c0 + c, __ldg(f + (size_t)c * P.n));
+        for (int k = P.width[0] + half; k < P.kpad[0]; k += 2) put(k, 0.f);   // zero the K padding
+    }
+
+    uint32_t phase = 0;
+    for (int l = 0; l < P.n_layers; ++l) {
+        const int cin = P.width[l], cout = P.width[l + 1], K = P.kpad[l], N = P.npad[l], wp4 = P.wpad4[l + 1];
+        // weights of this layer: packed Wt[k][wp4] (BN folded) -> w_hi/w_lo[k/4][n][4], zero padded
+        for (int t = tid; t < K * N; t += kTCThreads) {
+            const int k = t / N, nn = t - k * N;
+            const float v = (k < cin && nn < cout) ? __ldg(packed + P.woff[l] + k * wp4 + nn) : 0.f;
+            float h, lo_;
+            split_tf32(v, h, lo_);
+            const int off = ((k >> 2) * N + nn) * 4 + (k & 3);
+            w_hi[off] = h;
+            w_lo[off] = lo_;
+        }
+        for (int t = tid; t < kSAMaxC; t += kTCThreads) bsm[t] = t < cout ? __ldg(packed + P.boff[l] + t) : 0.f;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        const uint32_t tmem = tmem_base_s;
+        if (tid == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kSARows >> 4) << 24);
+            const uint32_t a_lbo = kSARows * 16, w_lbo = N * 16, sbo = 128;
+            for (int kk = 0; kk < K / 8; ++kk) {
+                const uint32_t aoff = kk * 2 * a_lbo, woff = kk * 2 * w_lbo;
+                const uint64_t ah = umma_desc_kmajor(smem_u32(a_hi) + aoff, a_lbo, sbo);
+                const uint64_t al = umma_desc_kmajor(smem_u32(a_lo) + aoff, a_lbo, sbo);
+                const uint64_t wh = umma_desc_kmajor(smem_u32(w_hi) + woff, w_lbo, sbo);
+                const uint64_t wl = umma_desc_kmajor(smem_u32(w_lo) + woff, w_lbo, sbo);
+                umma_tf32(tmem, ah, wh, idesc, kk > 0);
+                umma_tf32(tmem, al, wh, idesc, 1);
+                umma_tf32(tmem, ah, wl, idesc, 1);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+        }
+        {   // bounded wait for the MMAs of this layer
+            uint32_t done = 0;
+            for (int it = 0; it < (1 << 20) && !done; ++it)
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                             : "=r"(done) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
+            if (!done && tid == 0 && err) atomicExch(err, 1);
+            phase ^= 1u;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        // ---- epilogue: thread = one row (TMEM lane); warps w and w+4 split the columns ----------
+        const bool last = l + 1 == P.n_layers;
+        const int row = (warp & 3) * 32 + lane;
+        const int chalf = warp >> 2;                       // 0: columns [0, N/2), 1: [N/2, N)  (in 32-column chunks)
+        const int nchunks = (N + 31) / 32;
+        const int Knext = last ? 0 : P.kpad[l + 1];
+        for (int ch = chalf; ch < nchunks; ch += 2) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ch * 32;
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                         : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (!last) {
+                // bias + ReLU, split, store as next layer's A (columns >= cout are exact zeros: zero weights, zero bias)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int n0 = ch * 32 + q * 4;
+                    if (n0 < Knext) {
+                        float h[4], lo4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            split_tf32(fmaxf(__uint_as_float(v[q * 4 + e]) + bsm[n0 + e], 0.f), h[e], lo4[e]);
+                        const int off = ((n0 >> 2) * kSARows + row) * 4;
+                        *reinterpret_cast<float4 *>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+                        *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+                    }
+                }
+            } else {
+                // max over the nsample rows of a centre (values >= 0: bit patterns order like floats)
+                const unsigned gmask = S >= 32 ? 0xffffffffu : (((1u << S) - 1u) << ((lane / S) * S));
+                const int centre_local = row / S;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = ch * 32 + j;
+                    const unsigned bits = __float_as_uint(fmaxf(__uint_as_float(v[j]) + bsm[col < kSAMaxC ? col : 0], 0.f));
+                    const unsigned mx = __reduce_max_sync(gmask, bits);
+                    if (col < cout && (lane % (S >= 32 ? 32 : S)) == 0) atomicMax(&cmax[centre_local * kSAMaxC + col], mx);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncthreads();                                     // TMEM reads done before the next layer overwrites D
+    }
+    const int cout = P.width[P.n_layers];
+    for (int t = tid; t < cpb * cout; t += kTCThreads) {
+        const int ci = t / cout, col = t - ci * cout;
+        if (m0 + ci < P.m) out[((size_t)bi * cout + col) * P.m + m0 + ci] = __uint_as_float(cmax[ci * kSAMaxC + col]);
+    }
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_base_s), "r"(128));
+}
+
 }  // namespace pdm
 
 // packed: for each layer l, Wt[k][wpad(l+1)] (k < width[l]; transposed, BN folded, zero padded
@@ -197,6 +402,38 @@ extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample
     if (!xyz || !new_xyz || !idx || !packed || !out || (c_feat > 0 && !features))
         return fail(PDM_ERR_INVALID_ARG, "sa_fused_forward: null pointer");
     if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "sa_fused_forward: batch > 65535");
+    // tensor-core path (tcgen05): PDM_SA_TC=1 selects it, default is the CUDA-core kernel
+    {
+        const char *env = getenv("PDM_SA_TC");
+        const bool want_tc = env && env[0] == '1';
+        SATCParams T;
+        T.n = n; T.m = m; T.c_feat = c_feat; T.nsample = nsample; T.use_xyz = use_xyz ? 1 : 0; T.n_layers = n_layers;
+        int amax = 0, wmax = 0;
+        for (int l = 0; l <= n_layers; ++l) { T.width[l] = P.width[l]; T.wpad4[l] = P.wpad[l]; }
+        for (int l = 0; l < n_layers; ++l) {
+            T.kpad[l] = (P.width[l] + 7) / 8 * 8;
+            T.npad[l] = (P.width[l + 1] + 15) / 16 * 16;
+            T.woff[l] = P.woff[l];
+            T.boff[l] = P.boff[l];
+            amax = T.kpad[l] > amax ? T.kpad[l] : amax;
+            wmax = T.kpad[l] * T.npad[l] > wmax ? T.kpad[l] * T.npad[l] : wmax;
+        }
+        // layer l+1 reads what layer l's epilogue wrote: its K padding must be covered by layer l's N padding
+        bool ok = want_tc && nsample >= 8;
+        for (int l = 0; l + 1 < n_layers; ++l) ok = ok && T.kpad[l + 1] <= T.npad[l];
+        T.a_floats = amax * kSARows;
+        T.w_floats = wmax;
+        const int cpb = kSARows / nsample;
+        const size_t smem_tc = sizeof(float) * ((size_t)2 * T.a_floats + 2 * T.w_floats + kSAMaxC + (size_t)cpb * kSAMaxC) + 128;
+        if (ok && smem_tc <= 220 * 1024) {
+            if (int rc = ensure_dynamic_smem((const void *)sa_fused_tc_kernel, smem_tc)) return rc;
+            dim3 grid((m + cpb - 1) / cpb, b);
+            sa_fused_tc_kernel<<<grid, kTCThreads, smem_tc, (cudaStream_t)stream>>>(T, xyz, features, new_xyz, idx, packed, out, nullptr);
+            count_launch();
+            PDM_CHECK_LAUNCH("sa_fused_forward(tcgen05)");
+            return PDM_OK;
+        }
+    }
     const size_t smem = sizeof(float) * ((size_t)2 * P.act_floats + P.w_floats + kSAMaxC);
     if (int rc = ensure_dynamic_smem((const void *)sa_fused_kernel, smem)) return rc;
     const int cpb = kSARows / nsample;
