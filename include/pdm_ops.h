@@ -110,11 +110,17 @@ int pdm_query_and_group(int b, int c, int n, int npoints, int nsample, int use_x
  *   widths[0] = 3*use_xyz + c_feat; packed = per layer l the BN-folded weights transposed
  *   Wt[k][pad4(widths[l+1])] (k < widths[l], zero-padded columns) followed by the folded bias
  *   [pad4(widths[l+1])], all layers back to back (device, fp32)
+ *   packed_tc (optional, may be NULL) = the same weights prepared for the tcgen05 tensor-core
+ *   kernel: bias[n_layers][128], then per layer and per block of <= 64 output columns
+ *   W_hi[kpad/4][ns][4], W_lo[kpad/4][ns][4] (tf32-exact high part and fp32 remainder, K padded
+ *   to 8, N to 16, K-major core-matrix layout); when given and the scale fits, the layers run as
+ *   tcgen05.mma.kind::tf32 with hi*hi + lo*hi + hi*lo (fp32 accuracy), else on the CUDA cores
  *   -> out (B, widths[n_layers], M).
  * Limits: n_layers <= 4, every width <= 128, nsample a power of two in 4..128. */
 int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample, int use_xyz, const float *xyz,
                          const float *features, const float *new_xyz, const int *idx, int n_layers,
-                         const int *widths, const float *packed, float *out, void *stream);
+                         const int *widths, const float *packed, const float *packed_tc, float *out,
+                         void *stream);
 
 /* ---- PDM neck (SPEC_PDM.md) ---------------------------------------------------------- */
 

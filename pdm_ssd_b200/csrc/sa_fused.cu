@@ -181,16 +181,20 @@ sa_fused_kernel(SAFusedParams P, const float *__restrict__ xyz, const float *__r
 // The max-pool uses redux.sync on the bit patterns (values are >= 0 after ReLU).
 // Every mbarrier wait is bounded: a wrong descriptor can produce wrong numbers, never a hang.
 constexpr int kTCThreads = 256;
+constexpr int kTCSub = 64;         // output columns staged (and multiplied) at a time
 
+// Host-prepared operand buffer `packed_tc` (see pointnet2_modules._pack_folded_tc):
+//   bias[n_layers][128], then for every layer, for every block of <= 64 output columns:
+//   W_hi[kpad/4][ns][4], W_lo[kpad/4][ns][4]   -- already split and already in the MMA layout,
+// so staging a block is a straight 16-byte copy.
 struct SATCParams {
     int n, m, c_feat, nsample, use_xyz, n_layers;
     int width[kSAMaxLayers + 1];
     int kpad[kSAMaxLayers];        // input width of layer l rounded up to 8
     int npad[kSAMaxLayers];        // output width rounded up to 16
-    int wpad4[kSAMaxLayers + 1];   // packed-buffer padding (multiple of 4), as in SAFusedParams
-    int woff[kSAMaxLayers], boff[kSAMaxLayers];
+    int woff[kSAMaxLayers];        // offset (floats) of layer l's first block in packed_tc
     int a_floats;                  // floats of ONE of A_hi / A_lo
-    int w_floats;                  // floats of ONE of W_hi / W_lo
+    int w_floats;                  // floats of ONE of W_hi / W_lo (largest block)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -208,17 +212,16 @@ __device__ __forceinline__ void split_tf32(float v, float &hi, float &lo) {
     lo = v - hi;                                              // exact in fp32
 }
 
-__global__ void __launch_bounds__(kTCThreads, 1)
+__global__ void __launch_bounds__(kTCThreads, 3)
 sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__restrict__ feats,
                    const float *__restrict__ new_xyz, const int *__restrict__ idx,
-                   const float *__restrict__ packed, float *__restrict__ out, int *__restrict__ err) {
+                   const float *__restrict__ packed_tc, float *__restrict__ out, int *__restrict__ err) {
     extern __shared__ __align__(128) float smem[];
     float *a_hi = smem;
     float *a_lo = a_hi + P.a_floats;
     float *w_hi = a_lo + P.a_floats;
     float *w_lo = w_hi + P.w_floats;
-    float *bsm = w_lo + P.w_floats;                           // [128] bias of the current layer
-    unsigned *cmax = reinterpret_cast<unsigned *>(bsm + kSAMaxC);   // [centres per CTA][128] max-pool accumulators
+    unsigned *cmax = reinterpret_cast<unsigned *>(w_lo + P.w_floats);   // [centres per CTA][128] max-pool accumulators
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -237,85 +240,90 @@ sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__r
     }
     for (int t = tid; t < cpb * kSAMaxC; t += kTCThreads) cmax[t] = 0u;
 
-    // ---- gather the (xyz - centre, features) rows, split, store in the MMA layout -------------
+    // ---- gather the (xyz - centre, features) rows: 4 input channels -> one 16-byte store --------
     {
         const int r = tid & (kSARows - 1);
-        const int half = tid >> 7;
         const int i = r / S, sidx = r - i * S;
         const int mc = min(m0 + i, P.m - 1);
         const int id = __ldg(idx + ((size_t)bi * P.m + mc) * S + sidx);
-        auto put = [&](int k, float v) {
-            float h, l;
-            split_tf32(v, h, l);
-            const int off = ((k >> 2) * kSARows + r) * 4 + (k & 3);
-            a_hi[off] = h;
-            a_lo[off] = l;
-        };
-        int c0 = 0;
-        if (P.use_xyz) {
-            if (half == 0) {
-                const float *pp = xyz + ((size_t)bi * P.n + id) * 3;
-                const float *qq = new_xyz + ((size_t)bi * P.m + mc) * 3;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) put(a, __fsub_rn(__ldg(pp + a), __ldg(qq + a)));
-            }
-            c0 = 3;
-        }
+        const float *pp = xyz + ((size_t)bi * P.n + id) * 3;
+        const float *qq = new_xyz + ((size_t)bi * P.m + mc) * 3;
         const float *f = feats + (size_t)bi * P.c_feat * P.n + id;
-        for (int c = half; c < P.c_feat; c += 2) put(c0 + c, __ldg(f + (size_t)c * P.n));
-        for (int k = P.width[0] + half; k < P.kpad[0]; k += 2) put(k, 0.f);   // zero the K padding
+        const int c0 = P.use_xyz ? 3 : 0;
+        for (int k4 = (tid >> 7); k4 * 4 < P.kpad[0]; k4 += 2) {
+            float h[4], lo4[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int k = k4 * 4 + e;
+                float v = 0.f;                                   // K padding
+                if (k < c0) v = __fsub_rn(__ldg(pp + k), __ldg(qq + k));
+                else if (k < P.width[0]) v = __ldg(f + (size_t)(k - c0) * P.n);
+                split_tf32(v, h[e], lo4[e]);
+            }
+            const int off = (k4 * kSARows + r) * 4;
+            *reinterpret_cast<float4 *>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
+        }
     }
 
     uint32_t phase = 0;
     for (int l = 0; l < P.n_layers; ++l) {
-        const int cin = P.width[l], cout = P.width[l + 1], K = P.kpad[l], N = P.npad[l], wp4 = P.wpad4[l + 1];
-        // weights of this layer: packed Wt[k][wp4] (BN folded) -> w_hi/w_lo[k/4][n][4], zero padded
-        for (int t = tid; t < K * N; t += kTCThreads) {
-            const int k = t / N, nn = t - k * N;
-            const float v = (k < cin && nn < cout) ? __ldg(packed + P.woff[l] + k * wp4 + nn) : 0.f;
-            float h, lo_;
-            split_tf32(v, h, lo_);
-            const int off = ((k >> 2) * N + nn) * 4 + (k & 3);
-            w_hi[off] = h;
-            w_lo[off] = lo_;
-        }
-        for (int t = tid; t < kSAMaxC; t += kTCThreads) bsm[t] = t < cout ? __ldg(packed + P.boff[l] + t) : 0.f;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-        asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        const uint32_t tmem = tmem_base_s;
-        if (tid == 0) {
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kSARows >> 4) << 24);
-            const uint32_t a_lbo = kSARows * 16, w_lbo = N * 16, sbo = 128;
-            for (int kk = 0; kk < K / 8; ++kk) {
-                const uint32_t aoff = kk * 2 * a_lbo, woff = kk * 2 * w_lbo;
-                const uint64_t ah = umma_desc_kmajor(smem_u32(a_hi) + aoff, a_lbo, sbo);
-                const uint64_t al = umma_desc_kmajor(smem_u32(a_lo) + aoff, a_lbo, sbo);
-                const uint64_t wh = umma_desc_kmajor(smem_u32(w_hi) + woff, w_lbo, sbo);
-                const uint64_t wl = umma_desc_kmajor(smem_u32(w_lo) + woff, w_lbo, sbo);
-                umma_tf32(tmem, ah, wh, idesc, kk > 0);
-                umma_tf32(tmem, al, wh, idesc, 1);
-                umma_tf32(tmem, ah, wl, idesc, 1);
+        const int cout = P.width[l + 1], K = P.kpad[l], N = P.npad[l];
+        const float *bias = packed_tc + l * kSAMaxC;
+        const float *wsrc = packed_tc + P.woff[l];
+        for (int n0 = 0; n0 < N; n0 += kTCSub) {
+            const int ns = min(kTCSub, N - n0);
+            // stage this block of weights (pre-split, pre-laid-out): 2 * K * ns floats, 16 bytes at a time
+            const int blk4 = K * ns / 4;
+            const float4 *src_hi = reinterpret_cast<const float4 *>(wsrc);
+            const float4 *src_lo = src_hi + blk4;
+            for (int t = tid; t < blk4; t += kTCThreads) {
+                reinterpret_cast<float4 *>(w_hi)[t] = __ldg(src_hi + t);
+                reinterpret_cast<float4 *>(w_lo)[t] = __ldg(src_lo + t);
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
-        }
-        {   // bounded wait for the MMAs of this layer
-            uint32_t done = 0;
-            for (int it = 0; it < (1 << 20) && !done; ++it)
-                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                             : "=r"(done) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
-            if (!done && tid == 0 && err) atomicExch(err, 1);
+            wsrc += 2 * K * ns;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncthreads();
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            if (warp == 0) {
+                if (lane == 0) {
+                    const uint32_t tmem = tmem_base_s + n0;
+                    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ns >> 3) << 17) | ((uint32_t)(kSARows >> 4) << 24);
+                    const uint32_t a_lbo = kSARows * 16, w_lbo = ns * 16, sbo = 128;
+                    for (int kk = 0; kk < K / 8; ++kk) {
+                        const uint32_t aoff = kk * 2 * a_lbo, woff = kk * 2 * w_lbo;
+                        const uint64_t ah = umma_desc_kmajor(smem_u32(a_hi) + aoff, a_lbo, sbo);
+                        const uint64_t al = umma_desc_kmajor(smem_u32(a_lo) + aoff, a_lbo, sbo);
+                        const uint64_t wh = umma_desc_kmajor(smem_u32(w_hi) + woff, w_lbo, sbo);
+                        const uint64_t wl = umma_desc_kmajor(smem_u32(w_lo) + woff, w_lbo, sbo);
+                        umma_tf32(tmem, ah, wh, idesc, kk > 0);
+                        umma_tf32(tmem, al, wh, idesc, 1);
+                        umma_tf32(tmem, ah, wl, idesc, 1);
+                    }
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(&bar)) : "memory");
+                }
+                __syncwarp();
+                // bounded wait (warp 0 only; the others sleep in the barrier below): a wrong descriptor
+                // may give wrong numbers but never a hang
+                uint32_t done = 0;
+                for (int it = 0; it < (1 << 20) && !done; ++it)
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                                 : "=r"(done) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
+                if (!done && lane == 0 && err) atomicExch(err, 1);
+            }
             phase ^= 1u;
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncthreads();                                 // MMAs of this block complete: W may be overwritten, D is readable
+            asm volatile("tcgen05.fence::after_thread_sync;");
         }
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        // ---- epilogue: thread = one row (TMEM lane); warps w and w+4 split the columns ----------
+        // ---- epilogue: thread = one row (TMEM lane); warps w and w+4 split the 32-column chunks ----
         const bool last = l + 1 == P.n_layers;
         const int row = (warp & 3) * 32 + lane;
-        const int chalf = warp >> 2;                       // 0: columns [0, N/2), 1: [N/2, N)  (in 32-column chunks)
         const int nchunks = (N + 31) / 32;
         const int Knext = last ? 0 : P.kpad[l + 1];
-        for (int ch = chalf; ch < nchunks; ch += 2) {
+        const uint32_t tmem = tmem_base_s;
+        for (int ch = (warp >> 2); ch < nchunks; ch += 2) {
             uint32_t v[32];
             const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ch * 32;
             asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -332,10 +340,12 @@ sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__r
                 for (int q = 0; q < 8; ++q) {
                     const int n0 = ch * 32 + q * 4;
                     if (n0 < Knext) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4 *>(bias + n0));
+                        const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
                         float h[4], lo4[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e)
-                            split_tf32(fmaxf(__uint_as_float(v[q * 4 + e]) + bsm[n0 + e], 0.f), h[e], lo4[e]);
+                            split_tf32(fmaxf(__uint_as_float(v[q * 4 + e]) + bv[e], 0.f), h[e], lo4[e]);
                         const int off = ((n0 >> 2) * kSARows + row) * 4;
                         *reinterpret_cast<float4 *>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
                         *reinterpret_cast<float4 *>(a_lo + off) = make_float4(lo4[0], lo4[1], lo4[2], lo4[3]);
@@ -348,15 +358,17 @@ sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__r
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int col = ch * 32 + j;
-                    const unsigned bits = __float_as_uint(fmaxf(__uint_as_float(v[j]) + bsm[col < kSAMaxC ? col : 0], 0.f));
+                    const unsigned bits = __float_as_uint(fmaxf(__uint_as_float(v[j]) + __ldg(bias + col), 0.f));
                     const unsigned mx = __reduce_max_sync(gmask, bits);
                     if (col < cout && (lane % (S >= 32 ? 32 : S)) == 0) atomicMax(&cmax[centre_local * kSAMaxC + col], mx);
                 }
             }
         }
+        // (the next block's staging starts with fence + __syncthreads, which also orders these TMEM reads
+        //  and A stores before the next MMAs)
         asm volatile("tcgen05.fence::before_thread_sync;");
-        __syncthreads();                                     // TMEM reads done before the next layer overwrites D
     }
+    __syncthreads();
     const int cout = P.width[P.n_layers];
     for (int t = tid; t < cpb * cout; t += kTCThreads) {
         const int ci = t / cout, col = t - ci * cout;
@@ -369,10 +381,11 @@ sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__r
 
 // packed: for each layer l, Wt[k][wpad(l+1)] (k < width[l]; transposed, BN folded, zero padded
 // columns) followed by bias[wpad(l+1)]; offsets are derived here from `widths`.
+// packed_tc (optional): operands of the tensor-core kernel, see SATCParams.
 extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample, int use_xyz,
                                     const float *xyz, const float *features, const float *new_xyz,
                                     const int *idx, int n_layers, const int *widths,
-                                    const float *packed, float *out, void *stream) {
+                                    const float *packed, const float *packed_tc, float *out, void *stream) {
     using namespace pdm;
     if (b < 0 || n < 0 || m < 0 || c_feat < 0 || nsample <= 0)
         return fail(PDM_ERR_INVALID_ARG, "sa_fused_forward: bad size");
@@ -402,33 +415,42 @@ extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample
     if (!xyz || !new_xyz || !idx || !packed || !out || (c_feat > 0 && !features))
         return fail(PDM_ERR_INVALID_ARG, "sa_fused_forward: null pointer");
     if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "sa_fused_forward: batch > 65535");
-    // tensor-core path (tcgen05): PDM_SA_TC=1 selects it, default is the CUDA-core kernel
+    // tensor-core path (tcgen05) whenever its operands were supplied and the scale fits;
+    // PDM_SA_TC=0 forces the CUDA-core kernel
     {
         const char *env = getenv("PDM_SA_TC");
-        const bool want_tc = env && env[0] == '1';
+        const bool want_tc = packed_tc != nullptr && !(env && env[0] == '0');
         SATCParams T;
         T.n = n; T.m = m; T.c_feat = c_feat; T.nsample = nsample; T.use_xyz = use_xyz ? 1 : 0; T.n_layers = n_layers;
-        int amax = 0, wmax = 0;
-        for (int l = 0; l <= n_layers; ++l) { T.width[l] = P.width[l]; T.wpad4[l] = P.wpad[l]; }
+        int amax = 0, wmax = 0, woff = n_layers * kSAMaxC;
+        for (int l = 0; l <= n_layers; ++l) T.width[l] = P.width[l];
         for (int l = 0; l < n_layers; ++l) {
             T.kpad[l] = (P.width[l] + 7) / 8 * 8;
             T.npad[l] = (P.width[l + 1] + 15) / 16 * 16;
-            T.woff[l] = P.woff[l];
-            T.boff[l] = P.boff[l];
+            T.woff[l] = woff;
+            woff += 2 * T.kpad[l] * T.npad[l];
             amax = T.kpad[l] > amax ? T.kpad[l] : amax;
-            wmax = T.kpad[l] * T.npad[l] > wmax ? T.kpad[l] * T.npad[l] : wmax;
+            const int ns = T.npad[l] < kTCSub ? T.npad[l] : kTCSub;
+            wmax = T.kpad[l] * ns > wmax ? T.kpad[l] * ns : wmax;
         }
+        // Tensor cores only where the MLP is a genuine GEMM: below ~4k multiply-adds per row (SA1's
+        // 4-16-16-32 stack has 832) the tile is bound by the gather and the per-layer barriers and the
+        // CUDA-core kernel is faster (0.46 vs 0.70 ms at batch 16); SA2's 67-64-64-128 stack (16.6k)
+        // runs 1.6x faster on tcgen05 (0.56 vs 0.89 ms).  PDM_SA_TC=1 forces the tensor-core kernel.
+        long long macs_per_row = 0;
+        for (int l = 0; l < n_layers; ++l) macs_per_row += (long long)P.width[l] * P.width[l + 1];
+        const bool forced = env && env[0] == '1';
         // layer l+1 reads what layer l's epilogue wrote: its K padding must be covered by layer l's N padding
-        bool ok = want_tc && nsample >= 8;
+        bool ok = want_tc && nsample >= 8 && (forced || macs_per_row >= 4096);
         for (int l = 0; l + 1 < n_layers; ++l) ok = ok && T.kpad[l + 1] <= T.npad[l];
         T.a_floats = amax * kSARows;
         T.w_floats = wmax;
         const int cpb = kSARows / nsample;
-        const size_t smem_tc = sizeof(float) * ((size_t)2 * T.a_floats + 2 * T.w_floats + kSAMaxC + (size_t)cpb * kSAMaxC) + 128;
+        const size_t smem_tc = sizeof(float) * ((size_t)2 * T.a_floats + 2 * T.w_floats + (size_t)cpb * kSAMaxC);
         if (ok && smem_tc <= 220 * 1024) {
             if (int rc = ensure_dynamic_smem((const void *)sa_fused_tc_kernel, smem_tc)) return rc;
             dim3 grid((m + cpb - 1) / cpb, b);
-            sa_fused_tc_kernel<<<grid, kTCThreads, smem_tc, (cudaStream_t)stream>>>(T, xyz, features, new_xyz, idx, packed, out, nullptr);
+            sa_fused_tc_kernel<<<grid, kTCThreads, smem_tc, (cudaStream_t)stream>>>(T, xyz, features, new_xyz, idx, packed_tc, out, nullptr);
             count_launch();
             PDM_CHECK_LAUNCH("sa_fused_forward(tcgen05)");
             return PDM_OK;

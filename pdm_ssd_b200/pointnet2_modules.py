@@ -50,6 +50,28 @@ def _pack_folded(folded):
     return torch.cat(chunks).contiguous(), widths
 
 
+def _pack_folded_tc(folded):
+    """Operands of the tcgen05 kernel (layout documented at SATCParams in csrc/sa_fused.cu):
+    bias[L][128]; per layer, per block of <= 64 output columns: W_hi[K/4][ns][4], W_lo[K/4][ns][4] with
+    K padded to 8 and N to 16, hi = the 19 leading bits (what a tf32 operand keeps), lo = w - hi."""
+    L = len(folded)
+    bias = folded[0][0].new_zeros((L, 128))
+    chunks = []
+    for l, (w, b) in enumerate(folded):           # w (N, K)
+        n_out, k_in = w.shape
+        kpad, npad = (k_in + 7) // 8 * 8, (n_out + 15) // 16 * 16
+        wp = w.new_zeros((npad, kpad))
+        wp[:n_out, :k_in] = w
+        bias[l, :n_out] = b
+        hi = (wp.contiguous().view(torch.int32) & -8192).view(torch.float32)    # 0xffffe000
+        lo = wp - hi
+        for n0 in range(0, npad, 64):
+            for part in (hi, lo):
+                blk = part[n0:n0 + 64]                                         # (ns, kpad)
+                chunks.append(blk.reshape(blk.shape[0], kpad // 4, 4).permute(1, 0, 2).reshape(-1))
+    return torch.cat([bias.reshape(-1)] + chunks).contiguous()
+
+
 def _shared_mlp(widths: List[int]) -> nn.Sequential:
     """1x1 Conv2d(bias=False) + BatchNorm2d + ReLU per hop (pointnet2_modules.py:90-97,132-139)."""
     layers = []
@@ -112,10 +134,11 @@ class _PointnetSAModuleBase(nn.Module):
             if folded is None or len(folded) > 4 or max(max(w.shape) for w, _ in folded) > 128:
                 cache[si] = (version, xyz.new_zeros(1), None)
             else:
-                packed, widths = _pack_folded([(w.detach().float(), b.detach().float()) for w, b in folded])
-                cache[si] = (version, packed.to(xyz.device), widths)
+                fl = [(w.detach().float(), b.detach().float()) for w, b in folded]
+                packed, widths = _pack_folded(fl)
+                cache[si] = (version, packed.to(xyz.device), widths, _pack_folded_tc(fl).to(xyz.device))
             hit = cache[si]
-        _, packed, widths = hit
+        packed, widths, packed_tc = hit[1], hit[2], (hit[3] if len(hit) > 3 else None)
         if widths is None:
             return None
         B, N, _ = xyz.shape
@@ -132,7 +155,8 @@ class _PointnetSAModuleBase(nn.Module):
             rc = _lib.load().pdm_sa_fused_forward(
                 B, N, M, c_feat, S, 1 if grouper.use_xyz else 0, xyz.data_ptr(),
                 feats.data_ptr() if feats is not None else None, new_xyz.data_ptr(), idx.data_ptr(),
-                len(widths) - 1, warr, packed.data_ptr(), out.data_ptr(),
+                len(widths) - 1, warr, packed.data_ptr(),
+                packed_tc.data_ptr() if packed_tc is not None else None, out.data_ptr(),
                 torch.cuda.current_stream(xyz.device).cuda_stream)
         _lib.check(rc, "pdm_sa_fused_forward")
         return out
