@@ -139,6 +139,29 @@ int pdm_neck_forward(int batch, int p, int c, const float *point_coords, const f
                      const int *dilation, int sh_degree, float sigma, float eps,
                      float *spatial_features, int *dbg_keys, float *dbg_w, void *stream);
 
+/* ---- rotated BEV IoU / NMS (reference: pcdet/ops/iou3d_nms) ----------------------------------- */
+
+/* boxes_iou_bev_gpu (iou3d_nms_api.cpp:15, iou3d_nms.cpp:113-135, iou3d_nms_kernel.cu:279-293).
+ * boxes_a (Na,7), boxes_b (Nb,7) [x,y,z,dx,dy,dz,heading] -> ans_iou (Na,Nb). */
+int pdm_boxes_iou_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou,
+                      void *stream);
+
+/* boxes_overlap_bev_gpu (iou3d_nms_api.cpp:13, iou3d_nms.cpp:68-90, iou3d_nms_kernel.cu:236-249):
+ * overlap area instead of IoU, same shapes (used by boxes_iou3d_gpu, iou3d_nms_utils.py:47-82). */
+int pdm_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *boxes_b,
+                          float *ans_overlap, void *stream);
+
+/* nms_gpu (iou3d_nms_api.cpp:16, iou3d_nms.cpp:137-183, iou3d_nms_kernel.cu:295-341) for ALL frames
+ * of a batch in two launches and without the reference's per-call cudaMalloc, blocking D2H copy
+ * and host greedy loop: the greedy pass runs on the device.
+ *   boxes (frames,k,7) already sorted by descending score within each frame (the reference sorts
+ *   in torch first, iou3d_nms_utils.py:128-133); counts (frames) = valid boxes per frame, or NULL
+ *   when every frame has k; -> keep (frames,k) int32: positions of the kept boxes in ascending
+ *   order (= the reference's keep[:num_out]), padded with -1; num_keep (frames).
+ * Limit: k <= 4096. */
+int pdm_nms_bev_batched(int frames, int k, const float *boxes, const int *counts, float thresh,
+                        int *keep, int *num_keep, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,3 +143,22 @@ def three_interpolate_grad(grad_out, idx, weight, M):
     gp = np.zeros((B, C, M), dtype=np.float32)
     lib().oracle_three_interpolate_grad(B, C, N, M, _fp(grad_out), _ip(idx), _fp(weight), _fp(gp))
     return gp
+
+
+def boxes_iou_bev(boxes_a, boxes_b):
+    """(Na,7), (Nb,7) [x,y,z,dx,dy,dz,heading] -> (Na,Nb) rotated BEV IoU"""
+    a = np.ascontiguousarray(boxes_a, dtype=np.float32)
+    b = np.ascontiguousarray(boxes_b, dtype=np.float32)
+    out = np.empty((len(a), len(b)), dtype=np.float32)
+    lib().oracle_boxes_iou_bev(len(a), _fp(a), len(b), _fp(b), _fp(out))
+    return out
+
+
+def nms_bev(boxes_sorted, thresh):
+    """boxes (N,7) already sorted by descending score -> kept positions (ascending)"""
+    b = np.ascontiguousarray(boxes_sorted, dtype=np.float32)
+    keep = np.empty(len(b), dtype=np.int32)
+    fn = lib().oracle_nms_bev
+    fn.restype = ctypes.c_int
+    n = fn(len(b), _fp(b), ctypes.c_float(thresh), _ip(keep))
+    return keep[:n].copy()

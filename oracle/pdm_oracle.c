@@ -307,3 +307,121 @@ void oracle_three_interpolate_grad(int b, int c, int n, int m, const float *grad
             }
         }
 }
+
+/* =============================================================================================
+ * Rotated BEV IoU and greedy NMS -- restatement of pcdet/ops/iou3d_nms
+ * (paths relative to pcdet/ops/iou3d_nms/src/).  PINNED against the reference's own kernels
+ * (oracle/_ref/iou3d_nms_cuda_ref.so) on a B200: IoU to 1e-5 absolute (the device cos/sin/atan2 and
+ * nvcc's FMA contraction differ from libm in the last bits), keep lists identical on the
+ * committed golden cases (tests/golden/nms_*.npz).
+ * ============================================================================================= */
+typedef struct { float x, y; } pt2;
+
+/* iou3d_nms_kernel.cu:39-41 */
+static inline float nms_cross3(pt2 p1, pt2 p2, pt2 p0) {
+    return (p1.x - p0.x) * (p2.y - p0.y) - (p2.x - p0.x) * (p1.y - p0.y);
+}
+
+/* iou3d_nms_kernel.cu:51-60 check_in_box2d: point inside the box grown by a 1e-2 margin */
+static int nms_in_box(const float *box, pt2 p) {
+    const float MARGIN = 1e-2f;
+    const float c = cosf(-box[6]), s = sinf(-box[6]);
+    const float rx = (p.x - box[0]) * c + (p.y - box[1]) * (-s);
+    const float ry = (p.x - box[0]) * s + (p.y - box[1]) * c;
+    return fabsf(rx) < box[3] / 2 + MARGIN && fabsf(ry) < box[4] / 2 + MARGIN;
+}
+
+/* iou3d_nms_kernel.cu:62-91 intersection (with check_rect_cross :43-49) */
+static int nms_intersection(pt2 p1, pt2 p0, pt2 q1, pt2 q0, pt2 *ans) {
+    const float EPS = 1e-8f;
+    if (!(fminf(p0.x, p1.x) <= fmaxf(q0.x, q1.x) && fminf(q0.x, q1.x) <= fmaxf(p0.x, p1.x) &&
+          fminf(p0.y, p1.y) <= fmaxf(q0.y, q1.y) && fminf(q0.y, q1.y) <= fmaxf(p0.y, p1.y)))
+        return 0;
+    const float s1 = nms_cross3(q0, p1, p0), s2 = nms_cross3(p1, q1, p0);
+    const float s3 = nms_cross3(p0, q1, q0), s4 = nms_cross3(q1, p1, q0);
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return 0;
+    const float s5 = nms_cross3(q1, p1, p0);
+    if (fabsf(s5 - s1) > EPS) {
+        ans->x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        ans->y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        const float D = a0 * b1 - a1 * b0;
+        ans->x = (b0 * c1 - b1 * c0) / D;
+        ans->y = (a1 * c0 - a0 * c1) / D;
+    }
+    return 1;
+}
+
+static void nms_corners(const float *box, pt2 *c) {
+    /* iou3d_nms_kernel.cu:104-147: axis-aligned corners, then rotate_around_center (:93-97) */
+    const float hx = box[3] / 2, hy = box[4] / 2;
+    const float cs = cosf(box[6]), sn = sinf(box[6]);
+    const float px[4] = {box[0] - hx, box[0] + hx, box[0] + hx, box[0] - hx};
+    const float py[4] = {box[1] - hy, box[1] - hy, box[1] + hy, box[1] + hy};
+    for (int k = 0; k < 4; ++k) {
+        c[k].x = (px[k] - box[0]) * cs + (py[k] - box[1]) * (-sn) + box[0];
+        c[k].y = (px[k] - box[0]) * sn + (py[k] - box[1]) * cs + box[1];
+    }
+    c[4] = c[0];
+}
+
+/* iou3d_nms_kernel.cu:99-222 box_overlap */
+static float nms_box_overlap(const float *a, const float *b) {
+    pt2 ca[5], cb[5], pts[16], ctr = {0.f, 0.f};
+    int cnt = 0;
+    nms_corners(a, ca);
+    nms_corners(b, cb);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (nms_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], &pts[cnt])) {
+                ctr.x += pts[cnt].x; ctr.y += pts[cnt].y;
+                ++cnt;
+            }
+    for (int k = 0; k < 4; ++k) {
+        if (nms_in_box(a, cb[k])) { ctr.x += cb[k].x; ctr.y += cb[k].y; pts[cnt++] = cb[k]; }
+        if (nms_in_box(b, ca[k])) { ctr.x += ca[k].x; ctr.y += ca[k].y; pts[cnt++] = ca[k]; }
+    }
+    ctr.x /= cnt; ctr.y /= cnt;
+    for (int j = 0; j < cnt - 1; ++j)        /* bubble sort by atan2 around the centroid (:189-199) */
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (atan2f(pts[i].y - ctr.y, pts[i].x - ctr.x) > atan2f(pts[i + 1].y - ctr.y, pts[i + 1].x - ctr.x)) {
+                pt2 t = pts[i]; pts[i] = pts[i + 1]; pts[i + 1] = t;
+            }
+    float area = 0.f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        const float ux = pts[k].x - pts[0].x, uy = pts[k].y - pts[0].y;
+        const float vx = pts[k + 1].x - pts[0].x, vy = pts[k + 1].y - pts[0].y;
+        area += ux * vy - uy * vx;
+    }
+    return fabsf(area) / 2.0f;
+}
+
+/* iou3d_nms_kernel.cu:224-232 iou_bev */
+static float nms_iou_bev(const float *a, const float *b) {
+    const float sa = a[3] * a[4], sb = b[3] * b[4];
+    const float s = nms_box_overlap(a, b);
+    return s / fmaxf(sa + sb - s, 1e-8f);
+}
+
+/* iou3d_nms_kernel.cu:279-293 boxes_iou_bev_kernel */
+void oracle_boxes_iou_bev(int na, const float *a, int nb, const float *b, float *ans) {
+    for (int i = 0; i < na; ++i)
+        for (int j = 0; j < nb; ++j) ans[(size_t)i * nb + j] = nms_iou_bev(a + i * 7, b + j * 7);
+}
+
+/* nms_kernel (iou3d_nms_kernel.cu:295-341) + host greedy loop (iou3d_nms.cpp:159-176):
+ * boxes are already sorted by score; returns the number kept, keep[] = positions in that order. */
+int oracle_nms_bev(int n, const float *boxes, float thresh, int *keep) {
+    unsigned char *removed = (unsigned char *)calloc(n > 0 ? n : 1, 1);
+    int kept = 0;
+    for (int i = 0; i < n; ++i) {
+        if (removed[i]) continue;
+        keep[kept++] = i;
+        for (int j = i + 1; j < n; ++j)
+            if (!removed[j] && nms_iou_bev(boxes + i * 7, boxes + j * 7) > thresh) removed[j] = 1;
+    }
+    free(removed);
+    return kept;
+}

@@ -29,6 +29,9 @@ SIGNATURES = {
     "pdm_sa_fused_forward": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _vp, _vp, _vp, _vp],
     "pdm_neck_forward": [_i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f),
                          ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _f, _f, _vp, _vp, _vp, _vp],
+    "pdm_boxes_iou_bev": [_i, _vp, _i, _vp, _vp, _vp],
+    "pdm_boxes_overlap_bev": [_i, _vp, _i, _vp, _vp, _vp],
+    "pdm_nms_bev_batched": [_i, _i, _vp, _vp, _f, _vp, _vp, _vp],
 }
 
 _lib = None

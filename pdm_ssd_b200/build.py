@@ -21,6 +21,9 @@ FLAGS = [
     "--fmad=false",          # no implicit contraction: every fma in the kernels is spelled out
     "-Xptxas", "-v",
 ]
+# nms.cu restates arithmetic whose reference build uses nvcc's default contraction (iou3d_nms has
+# no -fmad flag, setup.py:63-72); keep decisions sit on `iou > thresh`, so it is compiled the same way
+DEFAULT_FMAD = {"nms.cu"}
 
 
 def sources():
@@ -44,7 +47,8 @@ def build(force=False, verbose=False):
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in sources():
         obj = os.path.join(HERE, "build", os.path.basename(src)[:-3] + ".o")
-        cmd = [NVCC] + [f for f in FLAGS if f != "-shared"] + ["-c", src, "-o", obj]
+        drop = {"-shared"} | ({"--fmad=false"} if os.path.basename(src) in DEFAULT_FMAD else set())
+        cmd = [NVCC] + [f for f in FLAGS if f not in drop] + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

@@ -1,0 +1,270 @@
+// nms.cu -- rotated bird's-eye-view IoU and greedy NMS, batched over frames, without host round trips.
+//
+// Reference: pcdet/ops/iou3d_nms (iou3d_nms_kernel.cu:99-234 box_overlap / iou_bev, :295-341
+// nms_kernel, iou3d_nms.cpp:137-183 nms_gpu).  There the suppression bit-mask is computed on the GPU,
+// copied to the host (cudaMalloc + blocking cudaMemcpy per call) and the greedy pass runs on the CPU,
+// once per frame (detector3d_template.py:199) -- a device synchronisation per frame and class.
+// Here one launch builds the masks of ALL frames (upper-triangular 64x64 tiles only: the greedy pass
+// never looks at a lower-indexed box again) and a second launch runs the greedy pass on the GPU, one
+// warp per frame with the "removed" bit set spread over the lanes and the mask rows prefetched.
+// The keep order is the reference's: ascending position in the score-sorted list.
+//
+// The overlap follows the reference's construction, margins included, so that keep decisions agree:
+// intersection points of the 4x4 edge pairs (bounding-box rejection, straddle test, EPS = 1e-8 branch
+// in the line intersection), corners of one box inside the other with a 1e-2 margin, the points
+// ordered by atan2 around their centroid (bubble sort), shoelace area; IoU = s / max(sa + sb - s, EPS).
+// This file is compiled with nvcc's default fused-multiply-add contraction (like the reference), not
+// with --fmad=false as the bit-exact sampling kernels are.
+#include "common.cuh"
+
+namespace pdm {
+
+constexpr float kNmsEps = 1e-8f;
+constexpr float kInBoxMargin = 1e-2f;
+constexpr int kTile = 64;  // boxes per mask tile = bits per mask word
+
+struct V2 {
+    float x, y;
+};
+__device__ __forceinline__ V2 mk(float x, float y) { V2 v; v.x = x; v.y = y; return v; }
+__device__ __forceinline__ float cross_o(const V2 &a, const V2 &b, const V2 &o) {
+    return (a.x - o.x) * (b.y - o.y) - (b.x - o.x) * (a.y - o.y);
+}
+
+// corners of a box [x, y, z, dx, dy, dz, heading] in the order (-,-), (+,-), (+,+), (-,+), rotated by heading
+__device__ __forceinline__ void box_corners(const float *box, V2 *c) {
+    const float hx = box[3] / 2, hy = box[4] / 2;
+    const float cs = cos(box[6]), sn = sin(box[6]);
+    const float px[4] = {box[0] - hx, box[0] + hx, box[0] + hx, box[0] - hx};
+    const float py[4] = {box[1] - hy, box[1] - hy, box[1] + hy, box[1] + hy};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        c[k].x = (px[k] - box[0]) * cs + (py[k] - box[1]) * (-sn) + box[0];
+        c[k].y = (px[k] - box[0]) * sn + (py[k] - box[1]) * cs + box[1];
+    }
+    c[4] = c[0];
+}
+
+__device__ __forceinline__ bool inside_with_margin(const float *box, const V2 &p) {
+    const float cs = cos(-box[6]), sn = sin(-box[6]);  // rotate the point into the box frame
+    const float rx = (p.x - box[0]) * cs + (p.y - box[1]) * (-sn);
+    const float ry = (p.x - box[0]) * sn + (p.y - box[1]) * cs;
+    return fabs(rx) < box[3] / 2 + kInBoxMargin && fabs(ry) < box[4] / 2 + kInBoxMargin;
+}
+
+// segment p0->p1 against q0->q1 (iou3d_nms_kernel.cu:62-91)
+__device__ __forceinline__ bool seg_intersection(const V2 &p1, const V2 &p0, const V2 &q1, const V2 &q0, V2 &out) {
+    const bool boxes_touch = fminf(p0.x, p1.x) <= fmaxf(q0.x, q1.x) && fminf(q0.x, q1.x) <= fmaxf(p0.x, p1.x) &&
+                             fminf(p0.y, p1.y) <= fmaxf(q0.y, q1.y) && fminf(q0.y, q1.y) <= fmaxf(p0.y, p1.y);
+    if (!boxes_touch) return false;
+    const float s1 = cross_o(q0, p1, p0);
+    const float s2 = cross_o(p1, q1, p0);
+    const float s3 = cross_o(p0, q1, q0);
+    const float s4 = cross_o(q1, p1, q0);
+    if (!(s1 * s2 > 0 && s3 * s4 > 0)) return false;
+    const float s5 = cross_o(q1, p1, p0);
+    if (fabs(s5 - s1) > kNmsEps) {
+        out.x = (s5 * q0.x - s1 * q1.x) / (s5 - s1);
+        out.y = (s5 * q0.y - s1 * q1.y) / (s5 - s1);
+    } else {
+        const float a0 = p0.y - p1.y, b0 = p1.x - p0.x, c0 = p0.x * p1.y - p1.x * p0.y;
+        const float a1 = q0.y - q1.y, b1 = q1.x - q0.x, c1 = q0.x * q1.y - q1.x * q0.y;
+        const float D = a0 * b1 - a1 * b0;
+        out.x = (b0 * c1 - b1 * c0) / D;
+        out.y = (a1 * c0 - a0 * c1) / D;
+    }
+    return true;
+}
+
+__device__ float bev_overlap(const float *a, const float *b) {
+    V2 ca[5], cb[5];
+    box_corners(a, ca);
+    box_corners(b, cb);
+    V2 pts[16];
+    int cnt = 0;
+    float sx = 0.f, sy = 0.f;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j)
+            if (seg_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], pts[cnt])) {
+                sx = sx + pts[cnt].x;
+                sy = sy + pts[cnt].y;
+                ++cnt;
+            }
+    for (int k = 0; k < 4; ++k) {
+        if (inside_with_margin(a, cb[k])) {
+            sx = sx + cb[k].x; sy = sy + cb[k].y;
+            pts[cnt++] = cb[k];
+        }
+        if (inside_with_margin(b, ca[k])) {
+            sx = sx + ca[k].x; sy = sy + ca[k].y;
+            pts[cnt++] = ca[k];
+        }
+    }
+    const V2 ctr = mk(sx / cnt, sy / cnt);
+    // ascending polar angle around the centroid: the reference bubble-sorts with atan2 evaluated inside
+    // every comparison (:189-199); the angles are pure functions of the points, so computing them once
+    // and carrying them through the same swaps gives the same order
+    float ang[16];
+    for (int k = 0; k < cnt; ++k) ang[k] = atan2(pts[k].y - ctr.y, pts[k].x - ctr.x);
+    for (int j = 0; j < cnt - 1; ++j)
+        for (int i = 0; i < cnt - j - 1; ++i)
+            if (ang[i] > ang[i + 1]) {
+                const V2 t = pts[i];
+                pts[i] = pts[i + 1];
+                pts[i + 1] = t;
+                const float ta = ang[i];
+                ang[i] = ang[i + 1];
+                ang[i + 1] = ta;
+            }
+    float area = 0.f;
+    for (int k = 0; k < cnt - 1; ++k) {
+        const V2 u = mk(pts[k].x - pts[0].x, pts[k].y - pts[0].y), v = mk(pts[k + 1].x - pts[0].x, pts[k + 1].y - pts[0].y);
+        area += u.x * v.y - u.y * v.x;
+    }
+    return fabs(area) / 2.0f;
+}
+
+__device__ __forceinline__ float bev_iou(const float *a, const float *b) {
+    const float sa = a[3] * a[4], sb = b[3] * b[4];
+    const float s = bev_overlap(a, b);
+    return s / fmaxf(sa + sb - s, kNmsEps);
+}
+
+// pairwise IoU (iou3d_nms_kernel.cu:279-293) or overlap area (:236-249): ans[i, j] = f(a_i, b_j)
+template <bool IOU>
+__global__ void __launch_bounds__(256)
+pair_bev_kernel(int na, const float *__restrict__ a, int nb, const float *__restrict__ b, float *__restrict__ ans) {
+    const int j = blockIdx.x * 16 + (threadIdx.x & 15), i = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (i >= na || j >= nb) return;
+    const float *pa = a + (size_t)i * 7, *pb = b + (size_t)j * 7;
+    ans[(size_t)i * nb + j] = IOU ? bev_iou(pa, pb) : bev_overlap(pa, pb);
+}
+
+// mask[f, i, w] bit t  <=>  IoU(box i, box 64w + t) > thresh, for 64w + t > i.  Upper-triangular tiles.
+__global__ void __launch_bounds__(kTile)
+nms_mask_kernel(int k, int words, const int *__restrict__ counts, float thresh, const float *__restrict__ boxes,
+                unsigned long long *__restrict__ mask) {
+    const int f = blockIdx.z, rt = blockIdx.y, ct = blockIdx.x;
+    const int n = counts ? min(__ldg(counts + f), k) : k;
+    const int i = rt * kTile + threadIdx.x;
+    unsigned long long bits = 0ull;
+    __shared__ float tile[kTile * 7];
+    const float *fb = boxes + (size_t)f * k * 7;
+    if (ct >= rt && rt * kTile < n && ct * kTile < n) {
+        const int cn = min(kTile, n - ct * kTile);
+        for (int t = threadIdx.x; t < cn * 7; t += kTile) tile[t] = __ldg(fb + (size_t)ct * kTile * 7 + t);
+        __syncthreads();
+        if (i < n) {
+            float me[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) me[q] = __ldg(fb + (size_t)i * 7 + q);
+            // Boxes whose circumscribed circles (grown by far more than the 1e-2 corner margin and any
+            // rounding) are disjoint have no edge crossing and no corner inside the other: the
+            // reference's overlap is then exactly 0 and `0 > thresh` is false for thresh >= 0.
+            const float my_r = 0.5f * sqrtf(me[3] * me[3] + me[4] * me[4]) * 1.001f + 0.1f;
+            for (int t = (ct == rt ? threadIdx.x + 1 : 0); t < cn; ++t) {
+                const float *ob = tile + t * 7;
+                const float ddx = ob[0] - me[0], ddy = ob[1] - me[1];
+                const float rr = my_r + 0.5f * sqrtf(ob[3] * ob[3] + ob[4] * ob[4]) * 1.001f + 0.1f;
+                if (thresh >= 0.f && ddx * ddx + ddy * ddy > rr * rr) continue;
+                if (bev_iou(me, ob) > thresh) bits |= 1ull << t;
+            }
+        }
+    }
+    if (i < k) mask[((size_t)f * k + i) * words + ct] = bits;
+}
+
+// Greedy pass, one warp per frame (iou3d_nms.cpp:159-176).  Lane l owns words l and l+32 of the
+// "removed" set (up to 4096 boxes); mask rows are prefetched a few iterations ahead.
+__global__ void __launch_bounds__(32)
+nms_sweep_kernel(int k, int words, const int *__restrict__ counts, const unsigned long long *__restrict__ mask,
+                 int *__restrict__ keep, int *__restrict__ num_keep) {
+    const int f = blockIdx.x, lane = threadIdx.x;
+    const int n = counts ? min(__ldg(counts + f), k) : k;
+    const unsigned long long *fm = mask + (size_t)f * k * words;
+    int *fk = keep + (size_t)f * k;
+    unsigned long long rem0 = 0ull, rem1 = 0ull;
+    constexpr int PF = 4;
+    unsigned long long r0[PF], r1[PF];
+#pragma unroll
+    for (int q = 0; q < PF; ++q) {
+        r0[q] = (q < n && lane < words) ? __ldg(fm + (size_t)q * words + lane) : 0ull;
+        r1[q] = (q < n && lane + 32 < words) ? __ldg(fm + (size_t)q * words + lane + 32) : 0ull;
+    }
+    int kept = 0;
+    for (int base = 0; base < n; base += PF) {
+#pragma unroll
+        for (int q = 0; q < PF; ++q) {
+            const int i = base + q;
+            const unsigned long long m0 = r0[q], m1 = r1[q];
+            const int nxt = i + PF;  // refill this slot for iteration i + PF
+            r0[q] = (nxt < n && lane < words) ? __ldg(fm + (size_t)nxt * words + lane) : 0ull;
+            r1[q] = (nxt < n && lane + 32 < words) ? __ldg(fm + (size_t)nxt * words + lane + 32) : 0ull;
+            if (i < n) {
+                const int w = i >> 6;
+                const unsigned long long word = __shfl_sync(0xffffffffu, w < 32 ? rem0 : rem1, w & 31);
+                if (!((word >> (i & 63)) & 1ull)) {   // warp-uniform
+                    if (lane == 0) fk[kept] = i;
+                    ++kept;
+                    rem0 |= m0;
+                    rem1 |= m1;
+                }
+            }
+        }
+    }
+    for (int t = kept + lane; t < k; t += 32) fk[t] = -1;
+    if (lane == 0) num_keep[f] = kept;
+}
+
+}  // namespace pdm
+
+extern "C" {
+
+static int pair_bev(bool iou, int na, const float *boxes_a, int nb, const float *boxes_b, float *ans, void *stream) {
+    using namespace pdm;
+    if (na < 0 || nb < 0) return fail(PDM_ERR_INVALID_ARG, "boxes_bev: negative size");
+    if (na == 0 || nb == 0) return PDM_OK;
+    if (!boxes_a || !boxes_b || !ans) return fail(PDM_ERR_INVALID_ARG, "boxes_bev: null pointer");
+    dim3 grid((nb + 15) / 16, (na + 15) / 16);
+    if (grid.y > 65535) return fail(PDM_ERR_UNSUPPORTED, "boxes_bev: too many boxes");
+    if (iou) pair_bev_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(na, boxes_a, nb, boxes_b, ans);
+    else pair_bev_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(na, boxes_a, nb, boxes_b, ans);
+    count_launch();
+    PDM_CHECK_LAUNCH("boxes_bev");
+    return PDM_OK;
+}
+
+int pdm_boxes_iou_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_iou, void *stream) {
+    return pair_bev(true, na, boxes_a, nb, boxes_b, ans_iou, stream);
+}
+
+int pdm_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *boxes_b, float *ans_overlap, void *stream) {
+    return pair_bev(false, na, boxes_a, nb, boxes_b, ans_overlap, stream);
+}
+
+int pdm_nms_bev_batched(int frames, int k, const float *boxes, const int *counts, float thresh, int *keep,
+                        int *num_keep, void *stream) {
+    using namespace pdm;
+    if (frames < 0 || k < 0) return fail(PDM_ERR_INVALID_ARG, "nms_bev_batched: negative size");
+    if (frames == 0) return PDM_OK;
+    if (!keep || !num_keep || (k > 0 && !boxes)) return fail(PDM_ERR_INVALID_ARG, "nms_bev_batched: null pointer");
+    if (k > 4096) return fail(PDM_ERR_UNSUPPORTED, "nms_bev_batched: at most 4096 boxes per frame (got %d)", k);
+    if (frames > 65535) return fail(PDM_ERR_UNSUPPORTED, "nms_bev_batched: too many frames");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int words = (k + kTile - 1) / kTile;
+    unsigned long long *mask = nullptr;
+    if (k > 0) {
+        mask = static_cast<unsigned long long *>(stream_scratch(st, (size_t)frames * k * words * sizeof(unsigned long long)));
+        if (!mask) return PDM_ERR_INVALID_ARG;
+        dim3 grid(words, words, frames);
+        nms_mask_kernel<<<grid, kTile, 0, st>>>(k, words, counts, thresh, boxes, mask);
+        count_launch();
+        PDM_CHECK_LAUNCH("nms_bev_batched(mask)");
+    }
+    nms_sweep_kernel<<<frames, 32, 0, st>>>(k, words, counts, mask, keep, num_keep);
+    count_launch();
+    PDM_CHECK_LAUNCH("nms_bev_batched(sweep)");
+    return PDM_OK;
+}
+
+}  // extern "C"

@@ -11,7 +11,8 @@ set ... target probability of detected boxes are calibrated through feature fusi
 closest in-tree pieces: CenterHead's shared 3x3 conv + heatmap branch with -2.19 bias
 (center_head.py:12-46,57-99) and PointHeadBox's FC stacks + PointResidualCoder.decode_torch
 (point_head_template.py:36-47, point_head_box.py:71-115, box_coder_utils.py:189-222).
-Rotated NMS (iou3d_nms) is the next row; post-processing here is score top-K.
+Post-processing is pcdet's class-agnostic rotated NMS (detector3d_template.py:199-254,
+model_nms_utils.py:6-25) for all frames at once on the device (`iou3d_nms_utils.batched_nms_gpu`).
 All dense layers are plain library convs/GEMMs (cuDNN/cuBLAS), fp32, TF32 off.
 """
 import math
@@ -21,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .backbone import AttrDict, PDMSSDBackbone
+from .iou3d_nms_utils import batched_nms_gpu
 from .pdm_neck import PDMNeck
 
 KITTI_MEAN_SIZE = [[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]]  # Car, Pedestrian, Cyclist (l,w,h)
@@ -38,6 +40,9 @@ def default_cfg(num_points=16384):
         MAP_TO_BEV=dict(NAME='PDMNeck', NUM_BEV_FEATURES=128, DILATION=[1, 1, 1], SH_DEGREE=2, SIGMA=0.8),
         BACKBONE_2D=dict(NUM_FILTERS=128, LAYER_NUM=2),
         DENSE_HEAD=dict(NAME='HybridHead', SHARED_CONV_CHANNEL=64, CLS_FC=[128], REG_FC=[128], MAX_OBJ_PER_SAMPLE=100),
+        # key names of detector3d_template.py:195-275 / model_nms_utils.py:15-20
+        POST_PROCESSING=dict(SCORE_THRESH=0.1, NMS_CONFIG=dict(
+            MULTI_CLASSES_NMS=False, NMS_TYPE='nms_gpu', NMS_THRESH=0.1, NMS_PRE_MAXSIZE=4096, NMS_POST_MAXSIZE=100)),
     )
 
 
@@ -70,8 +75,10 @@ def _fc(cin, widths, cout):
 
 
 class HybridHead(nn.Module):
-    def __init__(self, model_cfg, input_channels, point_channels, num_class, point_cloud_range, voxel_size):
+    def __init__(self, model_cfg, input_channels, point_channels, num_class, point_cloud_range, voxel_size,
+                 post_cfg=None):
         super().__init__()
+        self.post_cfg = post_cfg          # POST_PROCESSING block; None = score top-K without NMS
         self.num_class = num_class
         self.range = point_cloud_range
         self.voxel = voxel_size
@@ -119,11 +126,24 @@ class HybridHead(nn.Module):
                           cls_preds_normalized=True, heatmap=hm)
         # fixed-shape detections (B, K, 9) = box7, score, label -- ready for one NCCL gather
         M = best.numel() // B
-        k = min(self.topk, M)
-        top, idx = best.view(B, M).topk(k, dim=1)
-        gather = idx + (torch.arange(B, device=idx.device) * M)[:, None]
-        det = torch.cat([boxes[gather.flatten()].view(B, k, 7), top[..., None], label[gather.flatten()].view(B, k, 1).float() + 1], dim=2)
-        batch_dict['detections'] = det
+        if self.post_cfg is None:
+            k = min(self.topk, M)
+            top, idx = best.view(B, M).topk(k, dim=1)
+            valid = torch.ones_like(idx, dtype=torch.bool)
+        else:
+            # Detector3DTemplate.post_processing (detector3d_template.py:199-254) with class-agnostic NMS,
+            # for every frame in one pass and without leaving the device
+            nms = self.post_cfg.NMS_CONFIG
+            k = nms.NMS_POST_MAXSIZE
+            idx, num = batched_nms_gpu(boxes.view(B, M, 7), best.view(B, M), nms.NMS_THRESH, nms.NMS_PRE_MAXSIZE,
+                                       k, score_thresh=self.post_cfg.SCORE_THRESH)
+            valid = idx >= 0
+            idx = idx.clamp(min=0)
+            top = torch.gather(best.view(B, M), 1, idx)
+            batch_dict['num_detections'] = num
+        gather = (idx + (torch.arange(B, device=idx.device) * M)[:, None]).flatten()
+        det = torch.cat([boxes[gather].view(B, k, 7), top[..., None], label[gather].view(B, k, 1).float() + 1], dim=2)
+        batch_dict['detections'] = det * valid[..., None]      # rows past num_detections are zero (label 0)
         return batch_dict
 
 
@@ -140,7 +160,8 @@ class PDMSSD(nn.Module):
         self.map_to_bev_module = PDMNeck(neck_cfg)
         self.backbone_2d = BEVContext(cfg.BACKBONE_2D, self.map_to_bev_module.num_bev_features)
         self.dense_head = HybridHead(cfg.DENSE_HEAD, self.backbone_2d.num_bev_features, self.backbone_3d.num_point_features,
-                                     len(cfg.CLASS_NAMES), cfg.POINT_CLOUD_RANGE, cfg.VOXEL_SIZE)
+                                     len(cfg.CLASS_NAMES), cfg.POINT_CLOUD_RANGE, cfg.VOXEL_SIZE,
+                                     post_cfg=cfg.get('POST_PROCESSING'))
         self.module_list = [self.backbone_3d, self.map_to_bev_module, self.backbone_2d, self.dense_head]
 
     @torch.no_grad()

@@ -121,3 +121,30 @@ def to_pcdet_points(frames):
     B, N, C = frames.shape
     bidx = np.repeat(np.arange(B, dtype=np.float32), N)[:, None]
     return np.concatenate([bidx, frames.reshape(B * N, C)], 1)
+
+
+def random_boxes(n, seed=0, extent=35.0, clusters=None):
+    """(n, 7) float32 [x, y, z, dx, dy, dz, heading] in "score order" (row 0 = best): detector-like
+    candidates for NMS tests and benches.  With `clusters`, boxes are jittered copies of that many
+    objects (what a point-based head emits: many near-duplicate boxes per object); otherwise they
+    are spread uniformly over a square of half-width `extent` metres."""
+    rng = np.random.default_rng(4000 + seed)
+    sizes = np.array([[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]], np.float32)
+    b = np.zeros((n, 7), np.float32)
+    if clusters:
+        cx = rng.uniform(0, 2 * extent, clusters)
+        cy = rng.uniform(-extent, extent, clusters)
+        ch = rng.uniform(-np.pi, np.pi, clusters)
+        ck = rng.integers(0, 3, clusters)
+        which = rng.integers(0, clusters, n)
+        b[:, 0] = cx[which] + rng.normal(0, 0.3, n)
+        b[:, 1] = cy[which] + rng.normal(0, 0.3, n)
+        b[:, 3:6] = sizes[ck[which]] * rng.uniform(0.85, 1.15, (n, 3))
+        b[:, 6] = ch[which] + rng.normal(0, 0.15, n)
+    else:
+        b[:, 0] = rng.uniform(0, 2 * extent, n)
+        b[:, 1] = rng.uniform(-extent, extent, n)
+        b[:, 3:6] = sizes[rng.integers(0, 3, n)] * rng.uniform(0.8, 1.2, (n, 3))
+        b[:, 6] = rng.uniform(-np.pi, np.pi, n)
+    b[:, 2] = rng.uniform(-1.5, -0.5, n)
+    return b.astype(np.float32)

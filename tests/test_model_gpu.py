@@ -78,8 +78,22 @@ def test_detector_end_to_end_shapes_determinism_and_frame_independence():
     assert det.shape == (4, 100, 9) and torch.isfinite(det).all()
     assert out["spatial_features"].shape == (4, 128, 200, 176)
     assert out["batch_box_preds"].shape == (4 * 256, 7) and out["batch_cls_preds"].shape == (4 * 256, 3)
-    assert (det[..., 8] >= 1).all() and (det[..., 8] <= 3).all()
+    num = out["num_detections"].cpu()
+    assert (num >= 1).all() and (num <= 100).all()
+    for f in range(4):
+        d = det[f, :num[f]]
+        assert (d[:, 8] >= 1).all() and (d[:, 8] <= 3).all() and (d[:, 7] >= 0.1).all()
+        assert (det[f, num[f]:] == 0).all()                 # fixed shape, zero padded
     assert (det[:, :-1, 7] >= det[:, 1:, 7]).all()          # sorted by score
+    # same boxes as pcdet's per-frame post-processing (detector3d_template.py:199-254) on the head outputs
+    from pdm_ssd_b200 import model_nms_utils
+    nms_cfg = default_cfg().POST_PROCESSING.NMS_CONFIG
+    for f in range(4):
+        sc, _ = out["batch_cls_preds"][f * 256:(f + 1) * 256].max(dim=1)
+        bx = out["batch_box_preds"][f * 256:(f + 1) * 256]
+        sel, ssc = model_nms_utils.class_agnostic_nms(sc, bx, nms_cfg, score_thresh=0.1)
+        assert len(sel) == num[f]
+        assert torch.equal(bx[sel], det[f, :num[f], :7]) and torch.equal(ssc, det[f, :num[f], 7])
     again = model({"batch_size": 4, "points": pts})["detections"]
     assert torch.equal(det, again)                            # deterministic end to end
     # sharding by frame (what the multi-GPU path does) reproduces the batched result

@@ -1,0 +1,171 @@
+"""GPU parity tests of the rotated BEV IoU / NMS ops (C ABI via the reference-shaped Python API)
+against the CPU oracle, the golden vectors of the reference's kernels, and the reference's own
+compiled extension (oracle/_ref/iou3d_nms_cuda_ref.so) when present.  Keep lists must be identical."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from pdm_ssd_b200 import iou3d_nms_cuda as ours, iou3d_nms_utils as utils, model_nms_utils, synthetic
+from pdm_ssd_b200.backbone import AttrDict
+from test_nms_cpu import assert_keep_lists_agree
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "nms_*.npz")))
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+@pytest.fixture(scope="module")
+def ref_nms():
+    import build_ref
+    return build_ref.load_ref_nms()
+
+
+def our_keep(boxes, thresh):
+    b = _t(boxes)
+    keep = torch.zeros(len(boxes), dtype=torch.int64)
+    n = ours.nms_gpu(b, keep, thresh)
+    return keep[:n].numpy().astype(np.int32)
+
+
+@pytest.mark.parametrize("path", GOLD)
+def test_golden(path):
+    g = np.load(path)
+    boxes, thresh = g["boxes"], float(g["thresh"])
+    m = g["iou"].shape[0]
+    iou = utils.boxes_iou_bev(_t(boxes[:m]), _t(boxes[:m])).cpu().numpy()
+    np.testing.assert_allclose(iou, g["iou"], rtol=0, atol=1e-5)
+    ovl = torch.zeros((m, m), device=DEV)
+    ours.boxes_overlap_bev_gpu(_t(boxes[:m]), _t(boxes[:m]), ovl)
+    np.testing.assert_allclose(ovl.cpu().numpy(), g["overlap"], rtol=0, atol=1e-4)
+    assert np.array_equal(our_keep(boxes, thresh), g["keep"]), os.path.basename(path)
+
+
+def test_golden_present():
+    assert len(GOLD) >= 6
+
+
+@pytest.mark.parametrize("n,thresh,kw", [
+    (1, 0.1, {}), (2, 0.1, dict(extent=1.0)), (63, 0.3, dict(extent=5.0)), (64, 0.3, dict(extent=5.0)),
+    (65, 0.3, dict(extent=5.0)), (500, 0.1, dict(clusters=20)), (1000, 0.01, dict(clusters=50)),
+    (2047, 0.7, dict(clusters=80)), (4096, 0.1, dict(clusters=200)), (300, 0.0, {}), (300, 0.999, dict(clusters=5)),
+])
+def test_nms_vs_oracle_and_reference(ref_nms, n, thresh, kw):
+    boxes = synthetic.random_boxes(n, seed=n, **kw)
+    got = our_keep(boxes, thresh)
+    if ref_nms is not None:                       # the reference's kernels + host greedy loop, same GPU
+        keep = torch.zeros(n, dtype=torch.int64)
+        num = ref_nms.nms_gpu(_t(boxes), keep, float(thresh))
+        assert np.array_equal(got, keep[:num].numpy().astype(np.int32))
+    if n <= 1100:
+        assert_keep_lists_agree(boxes, thresh, got, oracle.nms_bev(boxes, thresh))
+
+
+def test_iou_vs_oracle_and_reference(ref_nms):
+    a = synthetic.random_boxes(333, seed=21, clusters=15)
+    b = synthetic.random_boxes(257, seed=22, clusters=15)
+    b[:100] = a[:100] + np.random.default_rng(0).normal(0, 0.05, (100, 7)).astype(np.float32)
+    got = utils.boxes_iou_bev(_t(a), _t(b)).cpu().numpy()
+
+    def close(x, y, atol):
+        # The construction is ill-conditioned for nearly coincident boxes (a straddle test or the 1e-2
+        # corner margin flips on a last-bit difference: the reference's own CPU and CUDA builds differ
+        # there too), so a handful of such pairs may move by ~1e-3; everything else must agree tightly.
+        d = np.abs(x - y)
+        assert (d > atol).mean() < 1e-4 and d.max() < 5e-3, (d.max(), (d > atol).sum())
+    close(got, oracle.boxes_iou_bev(a, b), 2e-5)
+    if ref_nms is not None:
+        want = torch.zeros((333, 257), device=DEV)
+        ref_nms.boxes_iou_bev_gpu(_t(a), _t(b), want)
+        close(got, want.cpu().numpy(), 1e-6)
+    assert (got > 0.3).sum() > 50
+
+
+def test_iou3d_matches_definition():
+    a = synthetic.random_boxes(200, seed=31, clusters=10)
+    got = utils.boxes_iou3d_gpu(_t(a), _t(a)).cpu().numpy()
+    assert np.allclose(np.diag(got), 1.0, atol=1e-4)
+    bev = oracle.boxes_iou_bev(a, a)
+    assert ((got > 0) <= (bev > 0)).all()
+
+
+def test_batched_counts_padding_and_frames():
+    F, K = 5, 300
+    boxes = np.stack([synthetic.random_boxes(K, seed=40 + f, clusters=12) for f in range(F)])
+    counts = np.array([300, 0, 1, 64, 177], np.int32)
+    keep = torch.full((F, K), 123, dtype=torch.int32, device=DEV)
+    num = torch.full((F,), -5, dtype=torch.int32, device=DEV)
+    ours.nms_bev_batched(_t(boxes), _t(counts), 0.2, keep, num)
+    keep, num = keep.cpu().numpy(), num.cpu().numpy()
+    for f in range(F):
+        want = oracle.nms_bev(boxes[f, :counts[f]], 0.2)
+        assert num[f] == len(want)
+        assert np.array_equal(keep[f, :num[f]], want)
+        assert (keep[f, num[f]:] == -1).all()
+    # no counts: all K boxes valid
+    keep2 = torch.empty((F, K), dtype=torch.int32, device=DEV)
+    num2 = torch.empty((F,), dtype=torch.int32, device=DEV)
+    ours.nms_bev_batched(_t(boxes), None, 0.2, keep2, num2)
+    assert np.array_equal(keep2[0, :num2[0]].cpu().numpy(), oracle.nms_bev(boxes[0], 0.2))
+
+
+def test_utils_nms_gpu_reference_semantics():
+    """iou3d_nms_utils.nms_gpu: unsorted boxes + scores, pre_maxsize (iou3d_nms_utils.py:120-135)."""
+    n = 700
+    boxes = synthetic.random_boxes(n, seed=51, clusters=25)
+    scores = np.random.default_rng(51).uniform(0, 1, n).astype(np.float32)
+    sel, _ = utils.nms_gpu(_t(boxes), _t(scores), 0.1, pre_maxsize=512)
+    order = np.argsort(-scores, kind="stable")[:512]
+    want = order[oracle.nms_bev(boxes[order], 0.1)]
+    assert np.array_equal(sel.cpu().numpy(), want)
+
+
+def test_class_agnostic_and_batched_agree():
+    F, M = 4, 1024
+    rng = np.random.default_rng(61)
+    boxes = np.stack([synthetic.random_boxes(M, seed=60 + f, clusters=30) for f in range(F)])
+    scores = rng.uniform(0, 1, (F, M)).astype(np.float32)
+    cfg = AttrDict(NMS_TYPE="nms_gpu", NMS_THRESH=0.1, NMS_PRE_MAXSIZE=512, NMS_POST_MAXSIZE=50)
+    sel, num = utils.batched_nms_gpu(_t(boxes), _t(scores), 0.1, 512, 50, score_thresh=0.3)
+    sel, num = sel.cpu().numpy(), num.cpu().numpy()
+    for f in range(F):
+        s, sc = model_nms_utils.class_agnostic_nms(_t(scores[f]), _t(boxes[f]), cfg, score_thresh=0.3)
+        s = s.cpu().numpy()
+        assert num[f] == len(s)
+        assert np.array_equal(sel[f, :num[f]], s)
+        assert (sel[f, num[f]:] == -1).all()
+        assert np.allclose(sc.cpu().numpy(), scores[f][s])
+
+
+def test_nms_graph_capture_and_stream():
+    F, K = 8, 512
+    boxes = _t(np.stack([synthetic.random_boxes(K, seed=70 + f, clusters=20) for f in range(F)]))
+    keep = torch.empty((F, K), dtype=torch.int32, device=DEV)
+    num = torch.empty((F,), dtype=torch.int32, device=DEV)
+    ours.nms_bev_batched(boxes, None, 0.1, keep, num)      # sizes the scratch eagerly
+    want = keep.clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        keep.fill_(0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            ours.nms_bev_batched(boxes, None, 0.1, keep, num)
+        g.replay()
+    s.synchronize()
+    assert torch.equal(keep, want)
+
+
+def test_errors():
+    with pytest.raises(RuntimeError):
+        ours.boxes_iou_bev_gpu(torch.zeros(3, 7), torch.zeros(3, 7), torch.zeros(3, 3))      # CPU tensors
+    with pytest.raises(RuntimeError):
+        ours.nms_bev_batched(torch.zeros((1, 5000, 7), device=DEV), None, 0.1,
+                             torch.empty((1, 5000), dtype=torch.int32, device=DEV),
+                             torch.empty((1,), dtype=torch.int32, device=DEV))               # k > 4096
