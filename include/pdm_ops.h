@@ -48,6 +48,17 @@ void pdm_reset_launch_count(void);
 int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                 void *stream);
 
+/* Scheduling hint for pdm_farthest_point_sampling (process-wide; no reference counterpart -- the
+ * reference has one kernel).  Results are bit-identical in every mode.
+ *   AUTO:       on-chip kernel (one frame per SM, lowest latency) unless one call has more frames than SMs
+ *   LATENCY:    always the on-chip kernel
+ *   THROUGHPUT: coordinates stay in L2, 2-3 frames share an SM: ~20 % longer per frame, about twice the
+ *               frames per second when many batches are in flight on several streams */
+#define PDM_FPS_MODE_AUTO 0
+#define PDM_FPS_MODE_LATENCY 1
+#define PDM_FPS_MODE_THROUGHPUT 2
+int pdm_set_fps_mode(int mode);
+
 /* gather_points_wrapper (pointnet2_api.cpp:16, sampling.cpp:14-23, sampling_gpu.cu:15-51).
  * points (B,C,N), idx (B,M) -> out (B,C,M). */
 int pdm_gather_points(int b, int c, int n, int npoints, const float *points, const int *idx,

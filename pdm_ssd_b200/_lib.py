@@ -16,6 +16,7 @@ _f = ctypes.c_float
 
 # name -> argtypes, mirrors include/pdm_ops.h one to one
 SIGNATURES = {
+    "pdm_set_fps_mode": [_i],
     "pdm_farthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
     "pdm_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pdm_gather_points_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
@@ -67,6 +68,14 @@ def check(rc, what):
     if rc != 0:
         msg = load().pdm_last_error().decode("utf-8", "replace")
         raise PdmOpsError("%s failed (code %d): %s" % (what, rc, msg))
+
+
+FPS_MODE_AUTO, FPS_MODE_LATENCY, FPS_MODE_THROUGHPUT = 0, 1, 2
+
+
+def set_fps_mode(mode):
+    """Scheduling hint for farthest point sampling (include/pdm_ops.h); results do not depend on it."""
+    check(load().pdm_set_fps_mode(int(mode)), "set_fps_mode")
 
 
 def launch_count():

@@ -392,6 +392,8 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     int *cend = reinterpret_cast<int *>(scratch + sz_grid + sz_cid);
     float4 *sorted = reinterpret_cast<float4 *>(scratch + sz_grid + sz_cid + sz_cend);
 
+    prefer_max_smem((const void *)bq_build_kernel);
+    prefer_max_smem((const void *)bq_query_kernel);
     bq_build_kernel<<<b, kBuildThreads, 0, st>>>(n, radius, cmax, xyz, grids, cid, cend, sorted);
     count_launch();
     cudaError_t e1 = cudaGetLastError();

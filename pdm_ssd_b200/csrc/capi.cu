@@ -1,6 +1,7 @@
 // capi.cu -- error plumbing and bookkeeping behind include/pdm_ops.h.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -34,6 +35,21 @@ int ensure_dynamic_smem(const void *func, size_t bytes) {
     if (e != cudaSuccess) return fail((int)e, "cudaFuncSetAttribute(%zu B): %s", bytes, cudaGetErrorString(e));
     cur = bytes;
     return PDM_OK;
+}
+
+void prefer_max_smem(const void *func) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, bool> done;
+    static const bool off = [] { const char *e = getenv("PDM_CARVEOUT"); return e && e[0] == 'o'; }();
+    if (off) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lock(mu);
+    bool &d = done[{func, dev}];
+    if (d) return;
+    d = true;
+    if (cudaFuncSetAttribute(func, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+        (void)cudaGetLastError();   // a hint only: never fail a launch over it
 }
 
 void *stream_scratch(cudaStream_t st, size_t bytes) {

@@ -59,6 +59,15 @@ __device__ __forceinline__ void st_cs_f1(float *p, float v) {
 // keeps driver calls out of the steady state (and out of CUDA-graph capture).
 int ensure_dynamic_smem(const void *func, size_t bytes);
 
+// cudaFuncAttributePreferredSharedMemoryCarveout = max shared, set once per (kernel, device).
+// The on-chip FPS kernel needs ~197 KB of shared memory per CTA; an SM can only take such a CTA in
+// the max-shared L1/shared split, and it has to drain before the split changes.  When the small
+// kernels of the chain (ball query, grouping, gather) run with their default (L1-heavy) preference
+// between FPS launches of other streams, the SMs keep flipping between the two splits and FPS CTAs
+// wait for drained SMs.  Asking for the same split everywhere removes the flips.
+// PDM_CARVEOUT=off disables it (A/B measurements).
+void prefer_max_smem(const void *func);
+
 // Persistent scratch, one buffer per (device, stream), grown on demand and never moved while in
 // use: work on one stream is serialised, so consecutive calls can share it, and a CUDA graph that
 // captured a call keeps a valid address (buffers that were outgrown are retired, not freed).

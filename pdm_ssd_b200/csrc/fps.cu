@@ -32,21 +32,9 @@
 // fps_generic_kernel: any n; same key trick, temp in global memory.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "fps_common.cuh"
 
 namespace pdm {
-
-constexpr unsigned kFull = 0xffffffffu;
-constexpr unsigned kPadKey = 0xffffffffu;  // tiekey of a padding slot: loses every tie
-
-__device__ __forceinline__ unsigned fps_tiekey(unsigned k, int p, unsigned bsmask) {
-    return p == 0 ? k : (__brev(k & bsmask) | (k >> p));
-}
-__device__ __forceinline__ unsigned fps_tiekey_inv(unsigned tk, int p, unsigned bsmask) {
-    if (p == 0) return tk;
-    const unsigned lowmask = (1u << (32 - p)) - 1u;
-    return ((tk & lowmask) << p) | (__brev(tk) & bsmask);
-}
 
 // ---------------------------------------------------------------------------------------
 // generic kernel
@@ -100,23 +88,6 @@ fps_generic_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__
 // ---------------------------------------------------------------------------------------
 // bucketed on-chip kernel
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned expand10(unsigned v) {  // 10 bits -> every third bit
-    v &= 0x3ffu;
-    v = (v | (v << 16)) & 0x030000ffu;
-    v = (v | (v << 8)) & 0x0300f00fu;
-    v = (v | (v << 4)) & 0x030c30c3u;
-    v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-// order-preserving float <-> uint map (for redux min/max over arbitrary-sign floats)
-__device__ __forceinline__ unsigned f2ord(float f) {
-    const unsigned u = __float_as_uint(f);
-    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float ord2f(unsigned u) {
-    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-
 template <int NW, int BPW, int KMAX>
 struct FpsSmem {
     static constexpr int CAP = NW * BPW * 32;
@@ -137,7 +108,6 @@ struct FpsSmem {
 // against 108 for redux + ballot + ffs + shfl.  The payload form is only valid when exactly one
 // lane holds the maximum; equal maxima (duplicate points) are detected with a ballot that runs
 // off the critical path and resolved by the smallest tiekey in a slow path.
-__device__ __forceinline__ bool multi_bit(unsigned ball) { return (ball & (ball - 1u)) != 0u; }
 
 // t[jj] for a warp-uniform runtime jj, with t[] in registers.  A 32-way switch around the
 // whole bucket update thrashed the instruction cache (20 KB loop), a flat 32-way select tree
@@ -209,8 +179,11 @@ __device__ __forceinline__ void reg_store(float (&t)[BPW], int jj, float v) {
 // TRACE: debug instantiation; frame 0 dumps clock64() stamps per round and warp into `trace`
 // ([round][warp][8] = t_start, t_afterA, t_afterB, t_afterC(before barrier), t_afterBarrier,
 //  t_afterPick1, t_afterLoop, K | nupdates<<8).
-template <int NW, int BPW, int KMAX, bool TRACE = false>
-__global__ void __launch_bounds__(NW * 32, 1)
+// LB: thread count promised to ptxas.  The kernel always runs NW*32 threads; promising more makes ptxas
+// budget fewer registers per thread (65536 / LB), which leaves register-file room on the SM for
+// CTAs of OTHER kernels (ball query, grouping) next to a resident FPS CTA -- see fps_dispatch.
+template <int NW, int BPW, int KMAX, bool TRACE = false, int LB = NW * 32>
+__global__ void __launch_bounds__(LB, 1)
 fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__restrict__ temp,
                   int *__restrict__ idxs, int *__restrict__ stats, long long *__restrict__ trace = nullptr) {
     using L = FpsSmem<NW, BPW, KMAX>;
@@ -266,49 +239,15 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
         lo[a] = ord2f(__reduce_min_sync(kFull, f2ord(l2)));
         hi[a] = ord2f(__reduce_max_sync(kFull, f2ord(h2)));
     }
-    // Spatial key.  Buckets are runs of 32 consecutive points in key order, and the pruning is as
-    // good as their boxes are tight.  LiDAR frames are nearly planar (KITTI: 70 x 80 x 4 m): there a
-    // 2-D Hilbert curve over the two long axes gives compact, jump-free runs (3.7 surviving buckets
-    // per sample against 5.2 for a 3-D Morton curve, measured on KITTI-shaped frames).  Volumetric
-    // clouds (shortest extent > 1/8 of the longest) keep the 3-D Morton key.
-    const float e0 = hi[0] - lo[0], e1 = hi[1] - lo[1], e2 = hi[2] - lo[2];
-    const float ext = fmaxf(fmaxf(e0, e1), e2);
-    const float emin = fminf(fminf(e0, e1), e2);
-    const bool planar = emin * 8.0f <= ext;
-    const int thin = (e2 <= e0 && e2 <= e1) ? 2 : ((e1 <= e0) ? 1 : 0);   // axis left out when planar
-    const int ax_u = thin == 0 ? 1 : 0, ax_v = thin == 2 ? 1 : 2;
-    const float inv = (ext > 0.f && ext < INFINITY) ? 1023.0f / ext : 0.f;
-    const float inv16 = (ext > 0.f && ext < INFINITY) ? 65535.0f / ext : 0.f;
+    FpsCurve curve;   // spatial sort code (fps_common.cuh)
+    curve.init(lo, hi);
 
     // ---- 2. keys -> shared, bitonic sort ---------------------------------------------------
     for (int k = tid; k < CAP; k += T) {
         unsigned long long key = ~0ull;
         if (k < n) {
             const float c[3] = {__ldg(dataset + k * 3 + 0), __ldg(dataset + k * 3 + 1), __ldg(dataset + k * 3 + 2)};
-            unsigned code;
-            if (planar) {
-                int iu = (int)((c[ax_u] - lo[ax_u]) * inv16), iv = (int)((c[ax_v] - lo[ax_v]) * inv16);  // NaN -> 0
-                unsigned x = (unsigned)max(0, min(65535, iu)), y = (unsigned)max(0, min(65535, iv));
-                unsigned d = 0u;
-#pragma unroll
-                for (int sft = 15; sft >= 0; --sft) {      // 16-bit 2-D Hilbert index (xy -> d)
-                    const unsigned rx = (x >> sft) & 1u, ry = (y >> sft) & 1u;
-                    d = (d << 2) | ((3u * rx) ^ ry);
-                    if (ry == 0u) {
-                        if (rx == 1u) { x = ~x; y = ~y; }  // reflect (only the low `sft` bits matter)
-                        const unsigned tswap = x; x = y; y = tswap;
-                    }
-                }
-                code = d;
-            } else {
-                unsigned q[3];
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    int qi = (int)((c[a] - lo[a]) * inv);  // NaN -> 0
-                    q[a] = (unsigned)max(0, min(1023, qi));
-                }
-                code = (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
-            }
+            const unsigned code = curve.code(c);
             key = ((unsigned long long)code << 32) | (unsigned)k;
         }
         keys[k] = key;
@@ -573,12 +512,13 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
     }
 }
 
-template <int NW, int BPW, int KMAX>
+template <int NW, int BPW, int KMAX, int LB = NW * 32>
 static int launch_bucket(int b, int n, int m, int p, const float *xyz, float *temp, int *idx,
                          int *stats, cudaStream_t st) {
     using L = FpsSmem<NW, BPW, KMAX>;
-    auto kern = fps_bucket_kernel<NW, BPW, KMAX>;
+    auto kern = fps_bucket_kernel<NW, BPW, KMAX, false, LB>;
     if (int rc = ensure_dynamic_smem((const void *)kern, L::kBytes)) return rc;
+    prefer_max_smem((const void *)kern);
     kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, stats, nullptr);
     count_launch();
     PDM_CHECK_LAUNCH("farthest_point_sampling(bucket)");
@@ -601,13 +541,21 @@ static int launch_cap(int nw, int kmax, int b, int n, int m, int p, const float 
                 CAP, nw, kmax);
 }
 
+static std::atomic<int> g_fps_mode{PDM_FPS_MODE_AUTO};
+
 static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, int *stats,
                         cudaStream_t st) {
     const int bs = ref_fps_block_size(n);
     int p = 0;
     while ((1 << p) < bs) ++p;
-    const char *force = getenv("PDM_FPS_KERNEL");  // "generic" | unset (debug/testing knob)
+    const char *force = getenv("PDM_FPS_KERNEL");  // "generic" | "l2" | "smem" | unset (debug/testing knob)
     const bool generic = force && force[0] == 'g';
+    // throughput variant (fps_l2.cu): asked for by the caller (pdm_set_fps_mode) or when one launch
+    // alone has more frames than the GPU has SMs
+    const int mode = g_fps_mode.load(std::memory_order_relaxed);
+    const bool want_l2 = force ? force[0] == 'l' : (mode == PDM_FPS_MODE_THROUGHPUT || (mode == PDM_FPS_MODE_AUTO && b > kNumSMs));
+    static const int l2_min_n = [] { const char *e = getenv("PDM_FPS_L2_MIN_N"); return e ? atoi(e) : 0; }();
+    if (!generic && want_l2 && n >= l2_min_n && fps_l2_supports(n)) return fps_l2_launch(b, n, m, p, xyz, temp, idx, stats, st);
     if (!generic && n >= 512 && n <= 16384) {
         // warps per CTA / samples per round: tuned on B200; PDM_FPS_NW / PDM_FPS_KMAX override
         const char *nwenv = getenv("PDM_FPS_NW"), *kenv = getenv("PDM_FPS_KMAX");
@@ -617,6 +565,12 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         if (n <= 2048) return launch_cap<2048>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
         if (n <= 4096) return launch_cap<4096>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
         if (n <= 8192) return launch_cap<8192>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
+        // 16384-point frames: 96 registers per thread (LB 544) measured as fast as the 128-register
+        // build and leaves a quarter of the register file to co-resident CTAs; PDM_FPS_LB=512 selects
+        // the 128-register build
+        const char *lbenv = getenv("PDM_FPS_LB");
+        if (nw == 16 && km == 8 && !(lbenv && atoi(lbenv) == 512))
+            return launch_bucket<16, 32, 8, 544>(b, n, m, p, xyz, temp, idx, stats, st);
         return launch_cap<16384>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
     }
     fps_generic_kernel<1024><<<b, 1024, 0, st>>>(n, m, p, xyz, temp, idx);
@@ -647,6 +601,13 @@ extern "C" int pdm_debug_fps_trace(int b, int n, int m, const float *xyz, float 
 extern "C" int pdm_debug_fps_rounds(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                     int *stats, void *stream) {
     return pdm::fps_dispatch(b, n, m, xyz, temp, idx, stats, (cudaStream_t)stream);
+}
+
+extern "C" int pdm_set_fps_mode(int mode) {
+    if (mode < PDM_FPS_MODE_AUTO || mode > PDM_FPS_MODE_THROUGHPUT)
+        return pdm::fail(PDM_ERR_INVALID_ARG, "set_fps_mode: unknown mode %d", mode);
+    pdm::g_fps_mode.store(mode);
+    return PDM_OK;
 }
 
 extern "C" int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp,

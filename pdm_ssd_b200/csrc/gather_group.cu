@@ -130,14 +130,17 @@ static int launch_group(int b, int c, int n, size_t cols, const float *points, c
     if (vec_ok) {
         const int cols4 = (int)(cols / 4);
         dim3 grid((cols4 + 255) / 256, chunks, b);
-        if (c >= CH)
+        if (c >= CH) {
+            prefer_max_smem((const void *)group_points_vec4_kernel<CH>);
             group_points_vec4_kernel<CH><<<grid, 256, 0, st>>>(c, n, cols4, points, idx, out);
-        else {
+        } else {
             grid.y = c;  // few channels: one per block row keeps registers low
+            prefer_max_smem((const void *)group_points_vec4_kernel<1>);
             group_points_vec4_kernel<1><<<grid, 256, 0, st>>>(c, n, cols4, points, idx, out);
         }
     } else {
         dim3 grid((unsigned)((cols + 255) / 256), chunks, b);
+        prefer_max_smem((const void *)group_points_scalar_kernel<CH>);
         group_points_scalar_kernel<CH><<<grid, 256, 0, st>>>(c, n, cols, points, idx, out);
     }
     count_launch();
@@ -192,6 +195,7 @@ int pdm_query_and_group(int b, int c, int n, int npoints, int nsample, int use_x
     if (b > 65535 || chunks > 65535) return fail(PDM_ERR_UNSUPPORTED, "query_and_group: b/c too large");
     const size_t cols = (size_t)npoints * nsample;
     dim3 grid((unsigned)((cols + 255) / 256), chunks, b);
+    prefer_max_smem((const void *)query_group_kernel<CH>);
     query_group_kernel<CH><<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, npoints, nsample, use_xyz ? 1 : 0, xyz,
                                                                   new_xyz, features, idx, out);
     count_launch();

@@ -139,11 +139,17 @@ class PipelinedSAChain:
     `capture(slot_args)` records each slot's step (all kernel launches, copies and the stream-ordered
     scratch allocations) into a CUDA graph bound to that slot's static input buffers; `submit()`
     then replays graphs, which removes the ~0.8 ms of Python/launch overhead per step that otherwise
-    bounds the pipeline once four or more batches are in flight."""
+    bounds the pipeline once four or more batches are in flight.
 
-    def __init__(self, batch, n_streams=4, n_points=16384, layers=KITTI_CHAIN, device="cuda:0", host=False, backend=None):
+    `fps_mode`: scheduling hint for farthest point sampling while the steps are captured / run
+    (`_lib.FPS_MODE_*`, include/pdm_ops.h).  With many batches in flight the THROUGHPUT kernel (several
+    frames per SM) gives more frames/s at a longer per-batch latency; results are bit-identical."""
+
+    def __init__(self, batch, n_streams=4, n_points=16384, layers=KITTI_CHAIN, device="cuda:0", host=False, backend=None,
+                 fps_mode=None):
         self.dev = torch.device(device)
         self.host = host
+        self.fps_mode = fps_mode
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_streams)]
         cls = HostSAChain if host else SAChain
         self.chains = [cls(batch, n_points, layers, self.dev, backend) for _ in range(n_streams)]
@@ -159,6 +165,16 @@ class PipelinedSAChain:
         assert len(slot_args) == len(self.streams)
         self.slot_args, self.graphs = list(slot_args), []
         torch.cuda.synchronize(self.dev)
+        if self.fps_mode is not None:
+            _lib.set_fps_mode(self.fps_mode)      # the captured graphs keep the kernels chosen now
+        try:
+            self._capture_all(_lib)
+        finally:
+            if self.fps_mode is not None:
+                _lib.set_fps_mode(_lib.FPS_MODE_AUTO)
+        torch.cuda.synchronize(self.dev)
+
+    def _capture_all(self, _lib):
         for st, chain, args in zip(self.streams, self.chains, self.slot_args):
             with torch.cuda.stream(st):
                 chain.run(*args)                      # warm-up: allocator pools, kernel attributes
@@ -170,7 +186,6 @@ class PipelinedSAChain:
             with torch.cuda.graph(g, stream=st):
                 chain.run(*args)
             self.graphs.append(g)
-        torch.cuda.synchronize(self.dev)
 
     def begin(self):
         """Fork: every worker stream waits for what is already queued on the current stream."""

@@ -44,6 +44,25 @@ def test_fps_golden(path):
     assert np.array_equal(temp, g["temp"]), "running-min scratch differs from the reference's"
 
 
+@pytest.mark.parametrize("n,m", [(16384, 4096), (4096, 1024), (5000, 700), (512, 512), (1000, 64)])
+def test_fps_throughput_mode_is_bit_identical(n, m):
+    """pdm_set_fps_mode(THROUGHPUT) selects fps_prepare + fps_l2_kernel (coordinates in L2, several
+    frames per SM): same indices, same final scratch contents as the on-chip kernel and the oracle."""
+    xyz = synthetic.kitti_batch(3, n, first_frame=n % 7)[..., :3].copy()
+    xyz[1, n // 2:] = xyz[1, :n - n // 2]                    # duplicates: tie-breaks on every path
+    want, want_t = our_fps(xyz, m, return_temp=True)
+    _lib.set_fps_mode(_lib.FPS_MODE_THROUGHPUT)
+    try:
+        got, got_t = our_fps(xyz, m, return_temp=True)
+    finally:
+        _lib.set_fps_mode(_lib.FPS_MODE_AUTO)
+    assert np.array_equal(got, want) and np.array_equal(got_t, want_t)
+    if n <= 5000:
+        assert np.array_equal(got, oracle.fps(xyz, m))
+    with pytest.raises(_lib.PdmOpsError):
+        _lib.set_fps_mode(7)
+
+
 def test_fps_golden_present(golden_dir):
     assert len(glob.glob(os.path.join(golden_dir, "fps_*.npz"))) >= 8
 

@@ -1,5 +1,6 @@
-"""Throughput of the SA chain with 1..12 batches in flight, eager launches vs CUDA graphs
-(device-resident and host end-to-end)."""
+"""Throughput of the SA chain with 1..N batches in flight, eager launches vs CUDA graphs
+(device-resident and host end-to-end).  SWEEP_STREAMS="12,16,24" / SWEEP_GRAPHS_ONLY=1 narrow the
+sweep; CUDA_DEVICE_MAX_CONNECTIONS (hardware work queues, default 8) is passed through."""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,9 +9,12 @@ import bench
 from pdm_ssd_b200.sa_chain import PipelinedSAChain
 dev = torch.device("cuda:0")
 steps = 96
+SS = tuple(int(x) for x in os.environ.get("SWEEP_STREAMS", "1,2,4,6,8,12").split(","))
+GG = (True,) if os.environ.get("SWEEP_GRAPHS_ONLY") else (False, True)
+print("CUDA_DEVICE_MAX_CONNECTIONS =", os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"))
 for hostmode in (False, True):
-    for graphs in (False, True):
-        for S in (1, 2, 4, 6, 8, 12):
+    for graphs in GG:
+        for S in SS:
             host = bench.make_host_batches(0, pool=S)
             if hostmode:
                 args = [(torch.from_numpy(f).pin_memory(), torch.from_numpy(g).pin_memory()) for f, g in host]
