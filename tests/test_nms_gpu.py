@@ -149,10 +149,12 @@ def test_nms_graph_capture_and_stream():
     boxes = _t(np.stack([synthetic.random_boxes(K, seed=70 + f, clusters=20) for f in range(F)]))
     keep = torch.empty((F, K), dtype=torch.int32, device=DEV)
     num = torch.empty((F,), dtype=torch.int32, device=DEV)
-    ours.nms_bev_batched(boxes, None, 0.1, keep, num)      # sizes the scratch eagerly
+    ours.nms_bev_batched(boxes, None, 0.1, keep, num)
     want = keep.clone()
     s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(s):
+        ours.nms_bev_batched(boxes, None, 0.1, keep, num)  # scratch is per stream: size it before capturing
         keep.fill_(0)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=s):
