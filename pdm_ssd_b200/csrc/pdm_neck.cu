@@ -6,18 +6,30 @@
 // round-to-nearest intrinsics in exactly the operation order of the spec, so the cell
 // coordinates / keys are bit-identical to the oracle's and the weights differ only through expf.
 //
+// Work is organised by COLUMN ENTRY ce = centre * Kxy + xy-offset: the Kz cells a centre dilates
+// into above one another belong to the same BEV pillar, and entry id e = ce * Kz + z-offset, so
+// "ascending e inside a cell" (the spec's summation order) is "ascending ce".  A pillar receives
+// ~5 column entries on KITTI-shaped input (16 cell entries), up to ~55 at close range.
+//
 // Pipeline (one stream, no host sync, no atomics on floating-point data):
-//   pdm_emit_kernel     thread per (centre, offset): cell, key3, weight w; histogram of key3
-//   pdm_scan_kernel     CTA per 4096-cell chunk: exclusive scan of the per-cell counts (chunk bases
-//                       from per-chunk counts the emit kernel accumulates), frame totals
-//   pdm_scatter_kernel  entry ids bucketed by cell (order inside a cell is arbitrary here ...)
-//   pdm_bev_kernel      CTA per (frame, y, 32-wide x tile), warp per pillar: walks the pillar's
-//                       cells in ascending z and each cell's entries in ASCENDING ENTRY ID
-//                       (... restored by a min-selection), so every sum is the serial in-order
-//                       fp32 sum the spec prescribes: F = sum(w f) / (sum|w| + eps), BEV = sum_z F.
-//                       Lanes own channels (coalesced 128-byte reads of feature rows); the tile is
-//                       transposed through shared memory so the (B,C,Y,X) output is written once,
-//                       in full 128-byte rows, zeros included (no memset pass, HBM-write bound).
+//   pdm_emit_kernel     thread per column entry: cells, key3 and weight of its Kz entries; pillar id
+//                       and base z cell of the column; histogram of column entries per pillar
+//   pdm_scan_kernel     CTA per chunk of 4096 pillars: exclusive scan of the pillar counts, compacted
+//                       list {start, count} of the occupied pillars, pillar -> compact row map
+//   pdm_scatter_kernel  column entries bucketed by pillar (arbitrary order inside a pillar)
+//   pdm_pillar_kernel   warp per OCCUPIED pillar, lanes = channels (16-byte loads of feature rows):
+//                       sorts the pillar's column entries (register bitonic network; counting sort
+//                       through scratch beyond 32), then walks the cells in ascending z and each
+//                       cell's entries in ascending id, so every sum is the serial in-order fp32
+//                       sum of the spec: F = sum(w f) / (sum|w| + eps), BEV = sum_z F  (w*f + acc is
+//                       one fma, the division one reciprocal per cell and a multiply).  Rows of a
+//                       centre are re-read for its other z cells from L1.  Writes one compact row
+//                       per occupied pillar.  All warps are independent: no barrier, no tile.
+//   pdm_dense_kernel    streams the dense (B,C,Y,X) map: thread per (pillar, 32 channels), every
+//                       element written once, plane by plane, zeros included (no memset pass;
+//                       HBM-write bound: 6.1 TB/s measured, 93 % of the copy peak).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pdm {
@@ -32,247 +44,378 @@ struct NeckCfg {
     float eps;
 };
 
-constexpr int kScanChunkFwd = 4096;
 constexpr float kSH0 = 0.28209479177387814f, kSH1 = 0.4886025119029199f, kSH2 = 1.0925484305920792f,
                 kSH3 = 0.31539156525252005f, kSH4 = 0.5462742152960396f;
 
+// Internal pillar id (y-major, so that the dense writer reads the pillars of an x tile contiguously):
+// pid = (b * Y + cy) * X + cx, global over the batch.  The API-visible key3 keeps the spec's x-major order.
+constexpr int kChunkShift = 12, kChunk = 1 << kChunkShift;   // pillars per scan CTA
+
 __global__ void __launch_bounds__(256)
-pdm_emit_kernel(int p_total, int K, int nsh, NeckCfg cfg, const float *__restrict__ coords,
+pdm_emit_kernel(int p_total, int batch, int kxy, int kz_n, int nsh, NeckCfg cfg, const float *__restrict__ coords,
                 const float *__restrict__ coef, int *__restrict__ keys, float *__restrict__ wts,
-                int *__restrict__ count, int *__restrict__ chunk_count, int chunks_per_frame) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long long)p_total * K) return;
-    const int p = (int)(e / K), o = (int)(e % K);
-    const int ny = 2 * cfg.dil[1] + 1, nz = 2 * cfg.dil[2] + 1;
-    const int ox = o / (ny * nz) - cfg.dil[0], oy = (o / nz) % ny - cfg.dil[1], oz = o % nz - cfg.dil[2];
+                int *__restrict__ colpid, int *__restrict__ colz, int *__restrict__ pcount,
+                int *__restrict__ chunk_e, int *__restrict__ chunk_o) {
+    const long long ce = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool inrange = ce < (long long)p_total * kxy;   // no early return: the warp votes below
+    const int p = inrange ? (int)(ce / kxy) : 0, oxy = inrange ? (int)(ce % kxy) : 0;
+    const int ny = 2 * cfg.dil[1] + 1;
+    const int off[2] = {oxy / ny - cfg.dil[0], oxy % ny - cfg.dil[1]};
     const float *pc = coords + (size_t)p * 4;
-    const int b = (int)__ldg(pc);
-    const float xyz[3] = {__ldg(pc + 1), __ldg(pc + 2), __ldg(pc + 3)};
-    const int off[3] = {ox, oy, oz};
-    int cell[3];
-    bool ok = true;
+    const int b = inrange ? (int)__ldg(pc) : -1;
+    const float xyz[3] = {inrange ? __ldg(pc + 1) : 0.f, inrange ? __ldg(pc + 2) : 0.f, inrange ? __ldg(pc + 3) : 0.f};
+    int c0[3];
+    bool ok = b >= 0 && b < batch;
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        const int c0 = (int)floorf(__fdiv_rn(__fsub_rn(xyz[a], cfg.rmin[a]), cfg.voxel[a]));
-        ok = ok && c0 >= 0 && c0 < cfg.grid[a];
-        cell[a] = c0 + off[a];
-        ok = ok && cell[a] >= 0 && cell[a] < cfg.grid[a];
+        c0[a] = (int)floorf(__fdiv_rn(__fsub_rn(xyz[a], cfg.rmin[a]), cfg.voxel[a]));
+        ok = ok && c0[a] >= 0 && c0[a] < cfg.grid[a];
     }
-    int key = -1;
-    float w = 0.f;
+    int cell[3] = {c0[0] + off[0], c0[1] + off[1], 0};
+    ok = ok && cell[0] >= 0 && cell[0] < cfg.grid[0] && cell[1] >= 0 && cell[1] < cfg.grid[1];
+    float dxy[2] = {0.f, 0.f}, cf[9];
     if (ok) {
-        key = ((b * cfg.grid[0] + cell[0]) * cfg.grid[1] + cell[1]) * cfg.grid[2] + cell[2];
-        float d[3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) {
+        for (int a = 0; a < 2; ++a) {
             const float ctr = __fadd_rn(__fmul_rn(__fadd_rn((float)cell[a], 0.5f), cfg.voxel[a]), cfg.rmin[a]);
-            d[a] = __fsub_rn(ctr, xyz[a]);
+            dxy[a] = __fsub_rn(ctr, xyz[a]);
         }
-        const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(d[0], d[0]), __fmul_rn(d[1], d[1])), __fmul_rn(d[2], d[2]));
-        const float nrm = __fsqrt_rn(__fadd_rn(r2, cfg.eps));
-        const float ux = __fdiv_rn(d[0], nrm), uy = __fdiv_rn(d[1], nrm), uz = __fdiv_rn(d[2], nrm);
-        const float *cf = coef + (size_t)p * nsh;
-        float acc = __fmul_rn(__ldg(cf), kSH0);
-        if (cfg.degree >= 1) {
-            acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + 1), __fmul_rn(kSH1, uy)));
-            acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + 2), __fmul_rn(kSH1, uz)));
-            acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + 3), __fmul_rn(kSH1, ux)));
-        }
-        if (cfg.degree >= 2) {
-            acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + 4), __fmul_rn(kSH2, __fmul_rn(ux, uy))));
-            acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + 5), __fmul_rn(kSH2, __fmul_rn(uy, uz))));
-            acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + 6),
-                                           __fmul_rn(kSH3, __fsub_rn(__fmul_rn(3.0f, __fmul_rn(uz, uz)), 1.0f))));
-            acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + 7), __fmul_rn(kSH2, __fmul_rn(ux, uz))));
-            acc = __fadd_rn(acc, __fmul_rn(__ldg(cf + 8),
-                                           __fmul_rn(kSH4, __fsub_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)))));
-        }
-        w = __fmul_rn(acc, expf(__fdiv_rn(-r2, cfg.two_sigma2)));
-        atomicAdd(&count[key], 1);
-        const int cpf = cfg.grid[0] * cfg.grid[1] * cfg.grid[2];
-        atomicAdd(&chunk_count[b * chunks_per_frame + (key - b * cpf) / kScanChunkFwd], 1);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) cf[q] = q < nsh ? __ldg(coef + (size_t)p * nsh + q) : 0.f;
     }
-    keys[e] = key;
-    wts[e] = w;
+    for (int ozi = 0; ozi < kz_n && inrange; ++ozi) {
+        cell[2] = c0[2] + ozi - cfg.dil[2];
+        const bool v = ok && cell[2] >= 0 && cell[2] < cfg.grid[2];
+        int key = -1;
+        float w = 0.f;
+        if (v) {
+            key = ((b * cfg.grid[0] + cell[0]) * cfg.grid[1] + cell[1]) * cfg.grid[2] + cell[2];
+            const float ctr = __fadd_rn(__fmul_rn(__fadd_rn((float)cell[2], 0.5f), cfg.voxel[2]), cfg.rmin[2]);
+            const float dz = __fsub_rn(ctr, xyz[2]);
+            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dxy[0], dxy[0]), __fmul_rn(dxy[1], dxy[1])), __fmul_rn(dz, dz));
+            const float nrm = __fsqrt_rn(__fadd_rn(r2, cfg.eps));
+            const float ux = __fdiv_rn(dxy[0], nrm), uy = __fdiv_rn(dxy[1], nrm), uz = __fdiv_rn(dz, nrm);
+            float acc = __fmul_rn(cf[0], kSH0);
+            if (cfg.degree >= 1) {
+                acc = __fadd_rn(acc, __fmul_rn(cf[1], __fmul_rn(kSH1, uy)));
+                acc = __fadd_rn(acc, __fmul_rn(cf[2], __fmul_rn(kSH1, uz)));
+                acc = __fadd_rn(acc, __fmul_rn(cf[3], __fmul_rn(kSH1, ux)));
+            }
+            if (cfg.degree >= 2) {
+                acc = __fadd_rn(acc, __fmul_rn(cf[4], __fmul_rn(kSH2, __fmul_rn(ux, uy))));
+                acc = __fadd_rn(acc, __fmul_rn(cf[5], __fmul_rn(kSH2, __fmul_rn(uy, uz))));
+                acc = __fadd_rn(acc, __fmul_rn(cf[6], __fmul_rn(kSH3, __fsub_rn(__fmul_rn(3.0f, __fmul_rn(uz, uz)), 1.0f))));
+                acc = __fadd_rn(acc, __fmul_rn(cf[7], __fmul_rn(kSH2, __fmul_rn(ux, uz))));
+                acc = __fadd_rn(acc, __fmul_rn(cf[8], __fmul_rn(kSH4, __fsub_rn(__fmul_rn(ux, ux), __fmul_rn(uy, uy)))));
+            }
+            w = __fmul_rn(acc, expf(__fdiv_rn(-r2, cfg.two_sigma2)));
+        }
+        keys[ce * kz_n + ozi] = key;
+        wts[ce * kz_n + ozi] = w;
+    }
+    // a column with a valid xy cell always holds an entry (its centre's own z cell is in range)
+    const int pid = ok ? (b * cfg.grid[1] + cell[1]) * cfg.grid[0] + cell[0] : -1;
+    const bool first = ok && atomicAdd(&pcount[pid], 1) == 0;
+    if (inrange) {
+        colpid[ce] = pid;
+        colz[ce] = c0[2];
+    }
+    // per-chunk totals for the scan (entries, occupied pillars): one atomic per distinct chunk per warp
+    const int lane = threadIdx.x & 31;
+    const int ch_e = ok ? pid >> kChunkShift : -1, ch_o = first ? pid >> kChunkShift : -1;
+    const unsigned pe = __match_any_sync(0xffffffffu, ch_e), po = __match_any_sync(0xffffffffu, ch_o);
+    if (ok && __ffs(pe) - 1 == lane) atomicAdd(&chunk_e[ch_e], __popc(pe));
+    if (first && __ffs(po) - 1 == lane) atomicAdd(&chunk_o[ch_o], __popc(po));
 }
 
-// Exclusive scan of the per-cell counts, in place and per frame.  The emit kernel also counts the
-// entries of every chunk of kScanChunk cells (chunk_count), so each CTA can scan one chunk
-// independently: its base is the sum of the earlier chunks of its frame.  CTA (chunk, frame).
-constexpr int kScanThreads = 256;
-constexpr int kScanChunk = kScanChunkFwd;   // cells per CTA: 16 per thread
+// CTA per chunk of 4096 pillars (4 consecutive pillars per thread, 16-byte loads): exclusive scan of
+// the column-entry counts -> pstart, compaction of the occupied pillars -> pslot (pillar -> compact row
+// or -1) and pinfo[row] = {start, count}.  Chunk bases come from the per-chunk totals the emit kernel
+// accumulated, so the chunks are independent.  The last chunk writes the number of occupied pillars.
+constexpr int kScanThreads = kChunk / 4;
 __global__ void __launch_bounds__(kScanThreads)
-pdm_scan_kernel(int cells_per_frame, int chunks_per_frame, int *__restrict__ count,
-                const int *__restrict__ chunk_count, int *__restrict__ totals) {
-    __shared__ int wsum[kScanThreads / 32];
-    __shared__ int base_s;
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int chunk = blockIdx.x, frame = blockIdx.y;
-    const int *cc = chunk_count + (size_t)frame * chunks_per_frame;
-    if (w == 0) {  // base = entries of the earlier chunks of this frame (and the frame total, once)
-        int s = 0, all = 0;
-        for (int q = lane; q < chunks_per_frame; q += 32) {
-            const int v = __ldg(cc + q);
-            all += v;
-            if (q < chunk) s += v;
-        }
-        s = __reduce_add_sync(0xffffffffu, s);
-        all = __reduce_add_sync(0xffffffffu, all);
-        if (lane == 0) {
-            base_s = s;
-            if (chunk == 0) totals[frame] = all;
-        }
-    }
-    int *c = count + (size_t)frame * cells_per_frame + (size_t)chunk * kScanChunk;
-    const int ncell = min(kScanChunk, cells_per_frame - chunk * kScanChunk);
-    constexpr int PER = kScanChunk / kScanThreads;
-    int v[PER];
-    int tsum = 0;
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        v[q] = (tid * PER + q < ncell) ? c[tid * PER + q] : 0;
-        tsum += v[q];
-    }
-    int incl = tsum;
+pdm_scan_kernel(int nchunks, const int *__restrict__ pcount, const int *__restrict__ chunk_e,
+                const int *__restrict__ chunk_o, int *__restrict__ pstart, int *__restrict__ pslot,
+                int2 *__restrict__ pinfo, int *__restrict__ totals) {
+    __shared__ int ws_e[32], ws_o[32], wb_e[32], wb_o[32];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, chunk = blockIdx.x;
+    int be = 0, bo = 0;   // base: totals of the earlier chunks
+    for (int q = tid; q < chunk; q += kScanThreads) be += __ldg(chunk_e + q), bo += __ldg(chunk_o + q);
+    be = __reduce_add_sync(0xffffffffu, be);
+    bo = __reduce_add_sync(0xffffffffu, bo);
+    const size_t i0 = (size_t)chunk * kChunk + tid * 4;
+    const int4 c = __ldg(reinterpret_cast<const int4 *>(pcount + i0));   // padded and zero-filled to whole chunks
+    const int se = c.x + c.y + c.z + c.w, so = (c.x > 0) + (c.y > 0) + (c.z > 0) + (c.w > 0);
+    int ie = se, io = so;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
+        const int ye = __shfl_up_sync(0xffffffffu, ie, o), yo = __shfl_up_sync(0xffffffffu, io, o);
+        if (lane >= o) ie += ye, io += yo;
     }
-    if (lane == 31) wsum[w] = incl;
+    if (lane == 31) ws_e[w] = ie, ws_o[w] = io;
+    if (lane == 0) wb_e[w] = be, wb_o[w] = bo;
     __syncthreads();
-    int run = base_s + incl - tsum;
-    for (int q = 0; q < w; ++q) run += wsum[q];
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        if (tid * PER + q < ncell) c[tid * PER + q] = run;
-        run += v[q];
+    {
+        int ve = ws_e[lane], vo = ws_o[lane];   // kScanThreads / 32 == 32 warps
+        const int te = __reduce_add_sync(0xffffffffu, wb_e[lane]), to = __reduce_add_sync(0xffffffffu, wb_o[lane]);
+        const int pre_e = __reduce_add_sync(0xffffffffu, lane < w ? ve : 0), pre_o = __reduce_add_sync(0xffffffffu, lane < w ? vo : 0);
+        be = te + pre_e + ie - se;
+        bo = to + pre_o + io - so;
+        if (chunk == nchunks - 1 && tid == kScanThreads - 1) {
+            totals[0] = be + se;   // column entries
+            totals[1] = bo + so;   // occupied pillars
+        }
     }
+    int4 st, sl;
+    const int cc[4] = {c.x, c.y, c.z, c.w};
+    int *stp = &st.x, *slp = &sl.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        stp[k] = be;
+        slp[k] = cc[k] > 0 ? bo : -1;
+        if (cc[k] > 0) pinfo[bo++] = make_int2(be, cc[k]);
+        be += cc[k];
+    }
+    *reinterpret_cast<int4 *>(pstart + i0) = st;
+    *reinterpret_cast<int4 *>(pslot + i0) = sl;
 }
 
 __global__ void __launch_bounds__(256)
-pdm_scatter_kernel(long long n_entries, int cells_per_frame, const int *__restrict__ keys,
-                   int *__restrict__ cursor, const int *__restrict__ totals, int *__restrict__ sorted) {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n_entries) return;
-    const int key = __ldg(keys + e);
-    if (key < 0) return;
-    const int b = key / cells_per_frame;
-    int base = 0;
-    for (int q = 0; q < b; ++q) base += __ldg(totals + q);
-    sorted[base + atomicAdd(&cursor[key], 1)] = (int)e;
+pdm_scatter_kernel(long long n_col, const int *__restrict__ colpid, const int *__restrict__ pstart,
+                   int *__restrict__ pcount, unsigned *__restrict__ sorted) {
+    const long long ce = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ce >= n_col) return;
+    const int pid = __ldg(colpid + ce);
+    if (pid < 0) return;
+    sorted[__ldg(pstart + pid) + atomicSub(&pcount[pid], 1) - 1] = (unsigned)ce;   // any order inside the pillar
 }
 
-constexpr int kBevWarps = 8;
-constexpr int kBevTileX = 32;
-constexpr int kCPL = 8;  // channels per lane per pass (256 channels per pass)
+// ---------------------------------------------------------------------------------------------------
+// per-pillar fusion
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPillarWarps = 8;
 
-__global__ void __launch_bounds__(kBevWarps * 32)
-pdm_bev_kernel(int c_total, int K, NeckCfg cfg, const float *__restrict__ feats, const float *__restrict__ wts,
-               const int *__restrict__ cend /*per-frame local exclusive ends after the scatter*/,
-               const int *__restrict__ totals, const int *__restrict__ sorted, float *__restrict__ bev) {
-    __shared__ float tile[kCPL * 32][kBevTileX + 1];
+// Work item = (occupied pillar, block of NG*32*VEC channels), one warp per item, lanes = channels.
+// VEC = 4: a lane owns 4 consecutive channels per group (16-byte loads; needs C % 4 == 0 and 16-byte
+// aligned rows); VEC = 1: any C.  The kernel is bound by instruction issue, not by memory (measured:
+// doubling the resident warps changed nothing, halving the per-pillar bookkeeping did), so the
+// bookkeeping is kept short: sort network only as wide as the pillar needs, no divisions in the
+// loops, and NG = 2 groups per warp when C > 128 so that a pillar is ordered and walked once.
+// A crowded pillar (> 32 column entries) is ordered through scratch by the warp of its first item,
+// which then does all of the pillar's channel blocks.
+template <int VEC, int NG, int UN /*feature rows in flight per warp*/, int MINB>
+__global__ void __launch_bounds__(kPillarWarps * 32, MINB)
+pdm_pillar_kernel(int c_total, int nblocks, int kxy, int kz_n, int kz, int Z, float eps,
+                  const float *__restrict__ feats, const float *__restrict__ wts, const int *__restrict__ colz,
+                  const int2 *__restrict__ pinfo, const int *__restrict__ totals, const unsigned *__restrict__ sorted,
+                  unsigned *sorted2, float *__restrict__ pf) {
+    constexpr int CH = 32 * VEC * NG;        // channels per item
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int X = cfg.grid[0], Y = cfg.grid[1], Z = cfg.grid[2];
-    const int b = blockIdx.z, cy = blockIdx.y, x0 = blockIdx.x * kBevTileX;
-    const int cells_per_frame = X * Y * Z;
-    int base = 0;
-    for (int q = 0; q < b; ++q) base += __ldg(totals + q);
-    const int *ce = cend + (size_t)b * cells_per_frame;
-    const int *srt = sorted + base;
+    const int nocc = __ldg(totals + 1);
 
-    for (int cb = 0; cb < c_total; cb += kCPL * 32) {  // 256 channels per pass
-        for (int px = w; px < kBevTileX; px += kBevWarps) {
-            const int cx = x0 + px;
-            float acc[kCPL];
+    for (int slot = blockIdx.x * kPillarWarps + w; slot < nocc; slot += gridDim.x * kPillarWarps) {
+        const int g0 = blockIdx.y;           // channel block of this warp (crowded pillars: block 0 does all)
+        const int2 info = __ldg(pinfo + slot);
+        const int start = info.x, n = info.y;
+        if (n > 32 && g0 > 0) continue;
+        float *orow = pf + (size_t)slot * c_total;
+
+        // ---- put the pillar's column entries in ascending order
+        unsigned ce = 0xffffffffu;      // n <= 32: lane r holds the r-th smallest
+        size_t prow = 0;                // ... the offset of its centre's feature row
+        int c0z = 0;                    // ... the z cell of that centre
+        float wz[3] = {0.f, 0.f, 0.f};  // ... and its weights, prefetched when the z dilation has <= 3 cells
+        if (n <= 32) {
+            if (lane < n) ce = __ldg(sorted + start + lane);
+            // bitonic network, only the stages a list of n needs (padding 0xffffffff sorts last)
+            for (int k = 2; (k >> 1) < n; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const unsigned o = __shfl_xor_sync(0xffffffffu, ce, j);
+                    const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+                    ce = keep_min ? min(ce, o) : max(ce, o);
+                }
+            }
+            if (lane < n) {
+                c0z = __ldg(colz + ce);
+                prow = (size_t)(ce / (unsigned)kxy) * c_total;
+                if (kz_n <= 3)
 #pragma unroll
-            for (int i = 0; i < kCPL; ++i) acc[i] = 0.f;
-            if (cx < X) {
-                const int cell0 = (cx * Y + cy) * Z;  // frame-local index of the pillar's z = 0 cell
-                // the pillar's Z cell ends are contiguous: fetched 32 at a time by the lanes in one
-                // coalesced load (a serial walk is Z dependent L2 round trips even for empty pillars)
-                int s = cell0 == 0 ? 0 : __ldg(ce + cell0 - 1);
-                for (int zb = 0; zb < Z; zb += 32) {
-                  const int zn = min(32, Z - zb);
-                  const int ends = lane < zn ? __ldg(ce + cell0 + zb + lane) : 0;
-                  const int last_end = __shfl_sync(0xffffffffu, ends, zn - 1);
-                  if (last_end == s) continue;          // nothing in these cells (most pillars)
-                  for (int zi = 0; zi < zn; ++zi) {
-                    const int e_end = __shfl_sync(0xffffffffu, ends, zi);
-                    if (e_end > s) {  // warp-uniform
-                        float num[kCPL];
+                    for (int q = 0; q < 3; ++q)
+                        if (q < kz_n) wz[q] = __ldg(wts + (size_t)ce * kz_n + q);
+            }
+        } else {
+            // ids are distinct, so rank = number of smaller ids (counting sort into scratch)
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const unsigned mine = i < n ? __ldg(sorted + start + i) : 0xffffffffu;
+                int rank = 0;
+                for (int j0 = 0; j0 < n; j0 += 32) {
+                    const unsigned other = j0 + lane < n ? __ldg(sorted + start + j0 + lane) : 0xffffffffu;
+                    const int jn = min(32, n - j0);
+                    for (int j = 0; j < jn; ++j) rank += __shfl_sync(0xffffffffu, other, j) < mine ? 1 : 0;
+                }
+                if (i < n) sorted2[start + rank] = mine;
+            }
+            __syncwarp();
+        }
+
+        for (int gb = g0; gb < (n > 32 ? nblocks : g0 + 1); ++gb) {
+            const int cb = gb * CH;
+            float acc[NG][VEC], num[NG][VEC];
+            bool cval[NG];
 #pragma unroll
-                        for (int i = 0; i < kCPL; ++i) num[i] = 0.f;
-                        float den = 0.f;
-                        const int cnt = e_end - s;
-                        if (cnt <= 32) {
-                            // usual case: one entry per lane; a bitonic network over the warp puts the
-                            // entry ids in ascending order (padding = 0xffffffff sorts last), then the
-                            // weights and row indices are fetched by all lanes at once and the rows
-                            // are streamed in order (their addresses are known up front, so the loads
-                            // of consecutive entries overlap; only the fp32 adds are serial).
-                            unsigned v = lane < cnt ? (unsigned)__ldg(srt + s + lane) : 0xffffffffu;
+            for (int g = 0; g < NG; ++g) {
+                cval[g] = cb + (g * 32 + lane) * VEC < c_total;
 #pragma unroll
-                            for (int k = 2; k <= 32; k <<= 1) {
+                for (int i = 0; i < VEC; ++i) acc[g][i] = 0.f, num[g][i] = 0.f;
+            }
+            float den = 0.f;
+            // lanes past the last channel read the block's first channels (in bounds) and never store
+            const float *fcol = feats + cb + (cb + lane * VEC < c_total ? lane * VEC : 0);
+
+            // entries of one chunk (<= 32, ascending, one per lane) that fall into cell z: add them in order
+            auto cell_pass = [&](int z, unsigned cev, size_t pr_l, int cz, bool live, bool pre, bool &any) {
+                const int dz = z - cz;
+                const bool in = live && dz >= -kz && dz <= kz;
+                unsigned mask = __ballot_sync(0xffffffffu, in);
+                if (!mask) return;
+                any = true;
+                float wq = 0.f;
+                if (pre) wq = dz + kz == 0 ? wz[0] : (dz + kz == 1 ? wz[1] : wz[2]);
+                else if (in) wq = __ldg(wts + (size_t)cev * kz_n + (dz + kz));
+                while (mask) {
+                    int src[UN];
+                    float fv[UN][NG][VEC];
+                    int cnt = 0;
 #pragma unroll
-                                for (int j = k >> 1; j > 0; j >>= 1) {
-                                    const unsigned o = __shfl_xor_sync(0xffffffffu, v, j);
-                                    const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
-                                    v = keep_min ? min(v, o) : max(v, o);
+                    for (int u = 0; u < UN; ++u) {
+                        src[u] = mask ? __ffs(mask) - 1 : 0;
+                        if (mask) { mask &= mask - 1; ++cnt; }
+                    }
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        if (u < cnt) {   // warp-uniform
+                            const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)pr_l, src[u]);
+                            const unsigned hi = __shfl_sync(0xffffffffu, (unsigned)(pr_l >> 32), src[u]);
+                            const float *f = fcol + (((size_t)hi << 32) | lo);
+#pragma unroll
+                            for (int g = 0; g < NG; ++g) {
+                                const float *fg = f + (cval[g] ? g * 32 * VEC : 0);
+                                if (VEC == 4) {
+                                    const float4 t = __ldg(reinterpret_cast<const float4 *>(fg));
+                                    fv[u][g][0] = t.x; fv[u][g][1 % VEC] = t.y; fv[u][g][2 % VEC] = t.z; fv[u][g][3 % VEC] = t.w;
+                                } else {
+                                    fv[u][g][0] = __ldg(fg);
                                 }
-                            }
-                            const float wq = lane < cnt ? __ldg(wts + v) : 0.f;
-                            const unsigned pq = lane < cnt ? v / (unsigned)K : 0u;
-#pragma unroll 2
-                            for (int it = 0; it < cnt; ++it) {
-                                const float wv = __shfl_sync(0xffffffffu, wq, it);
-                                const float *f = feats + (size_t)__shfl_sync(0xffffffffu, pq, it) * c_total + cb + lane;
-#pragma unroll
-                                for (int i = 0; i < kCPL; ++i)
-                                    if (cb + lane + 32 * i < c_total) num[i] = __fadd_rn(num[i], __fmul_rn(wv, __ldg(f + 32 * i)));
-                                den = __fadd_rn(den, fabsf(wv));
-                            }
-                        } else {
-                            // crowded cell: repeated min-selection over the unsorted list
-                            unsigned last = 0u;
-                            bool first = true;
-                            for (int it = s; it < e_end; ++it) {
-                                unsigned cand = 0xffffffffu;
-                                for (int q = s + lane; q < e_end; q += 32) {
-                                    const unsigned id = (unsigned)__ldg(srt + q);
-                                    if ((first || id > last) && id < cand) cand = id;
-                                }
-                                const unsigned id = __reduce_min_sync(0xffffffffu, cand);
-                                last = id;
-                                first = false;
-                                const float wv = __ldg(wts + id);
-                                const float *f = feats + (size_t)(id / (unsigned)K) * c_total + cb + lane;
-#pragma unroll
-                                for (int i = 0; i < kCPL; ++i)
-                                    if (cb + lane + 32 * i < c_total) num[i] = __fadd_rn(num[i], __fmul_rn(wv, __ldg(f + 32 * i)));
-                                den = __fadd_rn(den, fabsf(wv));
                             }
                         }
-                        const float dn = __fadd_rn(den, cfg.eps);
-#pragma unroll
-                        for (int i = 0; i < kCPL; ++i) acc[i] = __fadd_rn(acc[i], __fdiv_rn(num[i], dn));
                     }
-                    s = e_end;
-                  }
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        if (u < cnt) {
+                            const float wv = __shfl_sync(0xffffffffu, wq, src[u]);
+#pragma unroll
+                            for (int g = 0; g < NG; ++g)
+#pragma unroll
+                                for (int i = 0; i < VEC; ++i) num[g][i] = __fmaf_rn(wv, fv[u][g][i], num[g][i]);
+                            den = __fadd_rn(den, fabsf(wv));
+                        }
+                    }
+                }
+            };
+            auto cell_done = [&]() {   // F = num / (den + eps), added to the pillar in ascending z
+                const float rdn = __frcp_rn(__fadd_rn(den, eps));   // one reciprocal per cell instead of C divisions
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+#pragma unroll
+                    for (int i = 0; i < VEC; ++i) {
+                        acc[g][i] = __fmaf_rn(num[g][i], rdn, acc[g][i]);
+                        num[g][i] = 0.f;
+                    }
+                den = 0.f;
+            };
+
+            if (n <= 32) {
+                const bool live = lane < n;
+                const int zlo = max(0, __reduce_min_sync(0xffffffffu, live ? c0z : 0x7fffffff) - kz);
+                const int zhi = min(Z - 1, __reduce_max_sync(0xffffffffu, live ? c0z : (int)0x80000000) + kz);
+                for (int z = zlo; z <= zhi; ++z) {
+                    bool any = false;
+                    cell_pass(z, ce, prow, c0z, live, kz_n <= 3, any);
+                    if (any) cell_done();
+                }
+            } else {
+                for (int z = 0; z < Z; ++z) {
+                    bool any = false;
+                    for (int i0 = 0; i0 < n; i0 += 32) {
+                        const bool live = i0 + lane < n;
+                        const unsigned cev = live ? sorted2[start + i0 + lane] : 0u;   // plain load: written by this warp
+                        const int cz = live ? __ldg(colz + cev) : 0;
+                        cell_pass(z, cev, (size_t)(cev / (unsigned)kxy) * c_total, cz, live, false, any);
+                    }
+                    if (any) cell_done();
                 }
             }
 #pragma unroll
-            for (int i = 0; i < kCPL; ++i) tile[lane + 32 * i][px] = acc[i];
+            for (int g = 0; g < NG; ++g) {
+                if (cval[g]) {
+                    float *o = orow + cb + (g * 32 + lane) * VEC;
+                    if (VEC == 4) *reinterpret_cast<float4 *>(o) = make_float4(acc[g][0], acc[g][1 % VEC], acc[g][2 % VEC], acc[g][3 % VEC]);
+                    else *o = acc[g][0];
+                }
+            }
         }
-        __syncthreads();
-        // coalesced store: one 32-float row of the tile per (channel) -> bev[b, c, cy, x0 .. x0+31]
-        for (int r = w; r < kCPL * 32; r += kBevWarps) {
-            const int c = cb + r;
-            const int cx = x0 + lane;
-            if (c < c_total && cx < X) st_cs_f1(bev + (((size_t)b * c_total + c) * Y + cy) * X + cx, tile[r][lane]);
-        }
-        __syncthreads();
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dense BEV writer
+// ---------------------------------------------------------------------------------------------------
+// Thread = (pillar of a frame's flattened (cy, cx) plane, block of 32 channels): one 4-byte load of
+// the pillar's compact-row index, then -- occupied pillars only -- the row's 32 channels with eight
+// independent 16-byte loads, then 32 stores, one per channel plane: for a fixed channel a warp
+// writes 128 contiguous bytes and consecutive warps continue the same plane, so every plane is
+// written front to back.  Two dependent round trips per thread, everything else independent.
+// (Version 1 wrote 32-pillar x 256-channel tiles through shared memory: 128-byte pieces 140 KB
+// apart behind two barriers, 2.6 TB/s.  Version 2 gave a thread 4 pillars and transposed 4x4 blocks
+// in registers: its 8 load->store steps ran back to back, 8 round trips per warp, 3.2 TB/s.)
+// Zeros included: no memset pass.  No shared memory, no barrier.
+constexpr int kDenseCB = 32;
+
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+pdm_dense_kernel(int c_total, int plane /*Y*X*/, long long nthreads, const int *__restrict__ pslot,
+                 const float *__restrict__ pf, float *__restrict__ bev) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    const int cblocks = (c_total + kDenseCB - 1) / kDenseCB;
+    const int j = (int)(t % plane);
+    const int cb = (int)((t / plane) % cblocks) * kDenseCB, b = (int)(t / ((long long)plane * cblocks));
+    const int cn = min(kDenseCB, c_total - cb);
+    const int sl = __ldg(pslot + (size_t)b * plane + j);
+    float v[kDenseCB];
+#pragma unroll
+    for (int c = 0; c < kDenseCB; ++c) v[c] = 0.f;
+    if (sl >= 0) {
+        const float *r = pf + (size_t)sl * c_total + cb;
+        if (VEC) {   // C % 4 == 0
+#pragma unroll
+            for (int c = 0; c < kDenseCB; c += 4) {
+                if (c < cn) {
+                    const float4 q = __ldg(reinterpret_cast<const float4 *>(r + c));
+                    v[c] = q.x; v[c + 1] = q.y; v[c + 2] = q.z; v[c + 3] = q.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < kDenseCB; ++c)
+                if (c < cn) v[c] = __ldg(r + c);
+        }
+    }
+    float *out = bev + ((size_t)b * c_total + cb) * plane + j;
+#pragma unroll
+    for (int c = 0; c < kDenseCB; ++c)
+        if (c < cn) st_cs_f1(out + (size_t)c * plane, v[c]);
 }
 
 }  // namespace pdm
@@ -304,49 +447,88 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
     if (batch == 0 || c == 0) return PDM_OK;
     if (!spatial_features || (p > 0 && (!point_coords || !point_features || !coef)))
         return fail(PDM_ERR_INVALID_ARG, "neck_forward: null pointer");
-    if (grid[1] > 65535 || batch > 65535) return fail(PDM_ERR_UNSUPPORTED, "neck_forward: Y or batch > 65535");
     cudaStream_t st = (cudaStream_t)stream;
-    const int K = (2 * dilation[0] + 1) * (2 * dilation[1] + 1) * (2 * dilation[2] + 1);
+    const int kxy = (2 * dilation[0] + 1) * (2 * dilation[1] + 1), kz_n = 2 * dilation[2] + 1;
     const int nsh = (sh_degree + 1) * (sh_degree + 1);
-    const long long n_entries = (long long)p * K;
+    const long long n_col = (long long)p * kxy, n_entries = n_col * kz_n;
     if (n_entries >= 0x7fffffffLL) return fail(PDM_ERR_UNSUPPORTED, "neck_forward: too many entries");
+    const long long np_all = (long long)grid[0] * grid[1] * batch;   // pillars
+    const int nchunks = (int)((np_all + kChunk - 1) / kChunk);
+    const long long rows_max = np_all < n_col ? np_all : n_col;     // occupied pillars cannot exceed either
 
     auto align = [](size_t v) { return (v + 255) / 256 * 256; };
-    const size_t sz_keys = align((size_t)n_entries * 4 + 4), sz_w = sz_keys, sz_sorted = sz_keys;
-    const size_t sz_count = align((size_t)cells_per_frame * batch * 4);
-    const int chunks_per_frame = (int)((cells_per_frame + kScanChunk - 1) / kScanChunk);
-    const size_t sz_tot = align((size_t)batch * 4) + align((size_t)batch * chunks_per_frame * 4);
-    char *ws = static_cast<char *>(stream_scratch(st, sz_keys + sz_w + sz_sorted + sz_count + sz_tot));
+    const size_t sz_np = (size_t)nchunks * kChunk * 4;               // whole chunks: the scan loads 16 bytes per thread
+    const size_t sz_chunk = align((size_t)nchunks * 4);
+    const size_t sz_col = align((size_t)n_col * 4 + 4), sz_ent = align((size_t)n_entries * 4 + 4);
+    const size_t sz_info = align((size_t)rows_max * 8 + 8);
+    const size_t sz_pf = align((size_t)rows_max * c * 4 + 16);
+    const size_t total = 3 * sz_np + 2 * sz_chunk + 256 + 4 * sz_col + 2 * sz_ent + sz_info + sz_pf;
+    char *ws = static_cast<char *>(stream_scratch(st, total));
     if (!ws) return PDM_ERR_INVALID_ARG;  // message recorded by stream_scratch
-    int *keys = dbg_keys ? dbg_keys : reinterpret_cast<int *>(ws);
-    float *wts = dbg_w ? dbg_w : reinterpret_cast<float *>(ws + sz_keys);
-    int *sorted = reinterpret_cast<int *>(ws + sz_keys + sz_w);
-    int *count = reinterpret_cast<int *>(ws + sz_keys + sz_w + sz_sorted);
-    int *totals = reinterpret_cast<int *>(ws + sz_keys + sz_w + sz_sorted + sz_count);
-    int *chunk_count = reinterpret_cast<int *>(ws + sz_keys + sz_w + sz_sorted + sz_count + align((size_t)batch * 4));
-    cudaError_t err = cudaMemsetAsync(count, 0, sz_count + sz_tot, st);
-    if (err == cudaSuccess && n_entries > 0) {
-        pdm_emit_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(p, K, nsh, cfg, point_coords, coef, keys,
-                                                                           wts, count, chunk_count, chunks_per_frame);
+    char *q = ws;
+    auto take = [&](size_t bytes) { char *r = q; q += bytes; return r; };
+    int *pcount = reinterpret_cast<int *>(take(sz_np));            // zeroed region: pcount, chunk_e, chunk_o, totals
+    int *chunk_e = reinterpret_cast<int *>(take(sz_chunk));
+    int *chunk_o = reinterpret_cast<int *>(take(sz_chunk));
+    int *totals = reinterpret_cast<int *>(take(256));
+    int *pstart = reinterpret_cast<int *>(take(sz_np));
+    int *pslot = reinterpret_cast<int *>(take(sz_np));
+    int *colpid = reinterpret_cast<int *>(take(sz_col));
+    int *colz = reinterpret_cast<int *>(take(sz_col));
+    unsigned *sorted = reinterpret_cast<unsigned *>(take(sz_col));
+    unsigned *sorted2 = reinterpret_cast<unsigned *>(take(sz_col));
+    int *keys_ws = reinterpret_cast<int *>(take(sz_ent));
+    float *wts_ws = reinterpret_cast<float *>(take(sz_ent));
+    int2 *pinfo = reinterpret_cast<int2 *>(take(sz_info));
+    float *pf = reinterpret_cast<float *>(take(sz_pf));
+    int *keys = dbg_keys ? dbg_keys : keys_ws;
+    float *wts = dbg_w ? dbg_w : wts_ws;
+
+    cudaError_t err = cudaMemsetAsync(pcount, 0, sz_np + 2 * sz_chunk + 256, st);
+    if (err == cudaSuccess && n_col > 0) {
+        pdm_emit_kernel<<<(unsigned)((n_col + 255) / 256), 256, 0, st>>>(p, batch, kxy, kz_n, nsh, cfg, point_coords, coef,
+                                                                        keys, wts, colpid, colz, pcount, chunk_e, chunk_o);
         count_launch();
         err = cudaGetLastError();
     }
     if (err == cudaSuccess) {
-        pdm_scan_kernel<<<dim3(chunks_per_frame, batch), kScanThreads, 0, st>>>((int)cells_per_frame, chunks_per_frame,
-                                                                               count, chunk_count, totals);
+        pdm_scan_kernel<<<nchunks, kScanThreads, 0, st>>>(nchunks, pcount, chunk_e, chunk_o, pstart, pslot, pinfo, totals);
         count_launch();
         err = cudaGetLastError();
     }
-    if (err == cudaSuccess && n_entries > 0) {
-        pdm_scatter_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, st>>>(n_entries, (int)cells_per_frame, keys,
-                                                                              count, totals, sorted);
+    if (err == cudaSuccess && n_col > 0) {
+        pdm_scatter_kernel<<<(unsigned)((n_col + 255) / 256), 256, 0, st>>>(n_col, colpid, pstart, pcount, sorted);
+        count_launch();
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess && n_col > 0) {
+        const bool vec = (c % 4) == 0 && (reinterpret_cast<uintptr_t>(point_features) & 15) == 0;
+        const int ng = (vec ? c > 128 : c > 32) ? 2 : 1;
+        const int ch = 32 * (vec ? 4 : 1) * ng, nblocks = (c + ch - 1) / ch;
+        // a warp per (occupied pillar, channel block); the number of occupied pillars is only known on
+        // the device, so grid.x is sized for the SMs and strides over the pillars
+        long long need = (rows_max + kPillarWarps - 1) / kPillarWarps, cap = (kNumSMs * 16 + nblocks - 1) / nblocks;
+        dim3 g((unsigned)(need < cap ? need : cap), nblocks);
+        static const int minb = [] { const char *e = getenv("PDM_PILLAR_MINB"); return e ? atoi(e) : 0; }();   // A/B knob
+#define PDM_PILLAR(V, G, U, MB)                                                                                          \
+        pdm_pillar_kernel<V, G, U, MB><<<g, kPillarWarps * 32, 0, st>>>(c, nblocks, kxy, kz_n, dilation[2], grid[2], eps, \
+                                                                        point_features, wts, colz, pinfo, totals,      \
+                                                                        sorted, sorted2, pf)
+        if (vec && ng == 2 && minb == 2) PDM_PILLAR(4, 2, 4, 2);
+        else if (vec && ng == 2) PDM_PILLAR(4, 2, 2, 3);
+        else if (vec) PDM_PILLAR(4, 1, 4, 3);
+        else if (ng == 2) PDM_PILLAR(1, 2, 4, 4);
+        else PDM_PILLAR(1, 1, 4, 4);
+#undef PDM_PILLAR
         count_launch();
         err = cudaGetLastError();
     }
     if (err == cudaSuccess) {
-        dim3 g((grid[0] + kBevTileX - 1) / kBevTileX, grid[1], batch);
-        pdm_bev_kernel<<<g, kBevWarps * 32, 0, st>>>(c, K, cfg, point_features, wts, count, totals, sorted,
-                                                     spatial_features);
+        const int plane = grid[0] * grid[1], cblocks = (c + kDenseCB - 1) / kDenseCB;
+        const long long nthreads = (long long)batch * cblocks * plane;
+        const unsigned gx = (unsigned)((nthreads + 255) / 256);
+        if ((c % 4) == 0) pdm_dense_kernel<true><<<gx, 256, 0, st>>>(c, plane, nthreads, pslot, pf, spatial_features);
+        else pdm_dense_kernel<false><<<gx, 256, 0, st>>>(c, plane, nthreads, pslot, pf, spatial_features);
         count_launch();
         err = cudaGetLastError();
     }
