@@ -10,6 +10,8 @@
 // walks a chunk of CH channels with all CH*VEC gathers issued before the first store,
 // so each thread keeps up to 32 independent L2 requests in flight.  The reference
 // re-reads idx once per channel (grid.y = C); here it is read once per CH channels.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pdm {
@@ -116,6 +118,66 @@ query_group_kernel(int c, int n, int npoints, int nsample, int use_xyz, const fl
         if (c0 + k < c) st_cs_f1(dst + (size_t)k * cols, v[k]);
 }
 
+// Shared-memory variant for frames whose channel rows fit on chip (n <= 4096 with CHS = 2: SA2).
+// The gathers of the kernel above are 4-byte reads of 32 different cache lines per warp instruction,
+// and L1 looks up one line per cycle: 33.5 M gathered elements of SA2's (16,64,1024,32) tensor cost
+// ~115 us of L1 time for 25 us worth of HBM writes.  Here a CTA stages CHS channel rows of its frame
+// (or the frame's xyz) in shared memory with coalesced loads and gathers from there (a few bank
+// conflicts instead of 32 line look-ups), loops over all columns, 4 per thread (16-byte index loads
+// and 16-byte streaming stores).  grid.x = feature chunks [+ 1 for xyz], grid.y = frame.
+template <int CHS>
+__global__ void __launch_bounds__(512)
+query_group_smem_kernel(int c, int n, int npoints, int nsample, int use_xyz, const float *__restrict__ xyz,
+                        const float *__restrict__ new_xyz, const float *__restrict__ feats,
+                        const int *__restrict__ idx, float *__restrict__ out) {
+    extern __shared__ __align__(16) float qg_rows[];   // CHS * n floats, or 3 * n for the xyz CTA
+    const int bi = blockIdx.y, tid = threadIdx.x;
+    const size_t cols = (size_t)npoints * nsample;
+    const int cols4 = (int)(cols / 4);                 // host guarantees cols % 4 == 0, nsample % 4 == 0
+    const int ctot = (use_xyz ? 3 : 0) + c;
+    const int nchunks = (c + CHS - 1) / CHS;
+    const int4 *idx4 = reinterpret_cast<const int4 *>(idx + (size_t)bi * cols);
+    if ((int)blockIdx.x == nchunks) {                  // xyz - centre, three channels
+        const float *src = xyz + (size_t)bi * n * 3;
+        for (int t = tid; t < n * 3; t += blockDim.x) qg_rows[t] = __ldg(src + t);
+        __syncthreads();
+        float *dst = out + (size_t)bi * ctot * cols;
+        for (int q = tid; q < cols4; q += blockDim.x) {
+            const int4 id = __ldg(idx4 + q);
+            const float *cc = new_xyz + ((size_t)bi * npoints + (size_t)(q * 4) / nsample) * 3;   // the 4 columns share a centre
+            const float cx = __ldg(cc), cy = __ldg(cc + 1), cz = __ldg(cc + 2);
+            const int ids[4] = {id.x, id.y, id.z, id.w};
+            float v[3][4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                v[0][k] = __fsub_rn(qg_rows[ids[k] * 3 + 0], cx);
+                v[1][k] = __fsub_rn(qg_rows[ids[k] * 3 + 1], cy);
+                v[2][k] = __fsub_rn(qg_rows[ids[k] * 3 + 2], cz);
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+                st_cs_f4(dst + (size_t)a * cols + (size_t)q * 4, make_float4(v[a][0], v[a][1], v[a][2], v[a][3]));
+        }
+        return;
+    }
+    const int c0 = blockIdx.x * CHS;
+    const int cn = min(CHS, c - c0);
+    const float *src = feats + ((size_t)bi * c + c0) * n;
+    for (int t = tid; t < cn * n; t += blockDim.x) qg_rows[t] = __ldg(src + t);
+    __syncthreads();
+    float *dst = out + ((size_t)bi * ctot + (use_xyz ? 3 : 0) + c0) * cols;
+    for (int q = tid; q < cols4; q += blockDim.x) {
+        const int4 id = __ldg(idx4 + q);
+#pragma unroll
+        for (int k = 0; k < CHS; ++k) {
+            if (k < cn) {
+                const float *r = qg_rows + k * n;
+                st_cs_f4(dst + (size_t)k * cols + (size_t)q * 4, make_float4(r[id.x], r[id.y], r[id.z], r[id.w]));
+            }
+        }
+    }
+}
+
 static int launch_group(int b, int c, int n, size_t cols, const float *points, const int *idx,
                         float *out, cudaStream_t st, const char *what) {
     if (b < 0 || c < 0 || n < 0) return fail(PDM_ERR_INVALID_ARG, "%s: negative size", what);
@@ -194,6 +256,23 @@ int pdm_query_and_group(int b, int c, int n, int npoints, int nsample, int use_x
     const int chunks = (c + CH - 1) / CH + (use_xyz ? 1 : 0);
     if (b > 65535 || chunks > 65535) return fail(PDM_ERR_UNSUPPORTED, "query_and_group: b/c too large");
     const size_t cols = (size_t)npoints * nsample;
+    {
+        // channel rows in shared memory when they fit and there is enough to gather (see the kernel)
+        constexpr int CHS = 2;
+        const size_t smem = (size_t)n * 4 * (use_xyz ? 3 : CHS);
+        static const bool off = [] { const char *e = getenv("PDM_QG_SMEM"); return e && e[0] == 'o'; }();   // A/B knob
+        if (!off && c >= 8 && smem <= 64 * 1024 && nsample % 4 == 0 && cols < 0x7fffffffu &&
+            ((reinterpret_cast<uintptr_t>(idx) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+            auto kern = query_group_smem_kernel<CHS>;
+            if (int rc = ensure_dynamic_smem((const void *)kern, smem)) return rc;
+            dim3 grid((c + CHS - 1) / CHS + (use_xyz ? 1 : 0), b);
+            kern<<<grid, 512, smem, (cudaStream_t)stream>>>(c, n, npoints, nsample, use_xyz ? 1 : 0, xyz, new_xyz,
+                                                           features, idx, out);
+            count_launch();
+            PDM_CHECK_LAUNCH("query_and_group(smem)");
+            return PDM_OK;
+        }
+    }
     dim3 grid((unsigned)((cols + 255) / 256), chunks, b);
     prefer_max_smem((const void *)query_group_kernel<CH>);
     query_group_kernel<CH><<<grid, 256, 0, (cudaStream_t)stream>>>(c, n, npoints, nsample, use_xyz ? 1 : 0, xyz,
