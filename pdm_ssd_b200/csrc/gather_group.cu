@@ -189,6 +189,21 @@ static int launch_group(int b, int c, int n, size_t cols, const float *points, c
     if (chunks > 65535) return fail(PDM_ERR_UNSUPPORTED, "%s: too many channels %d", what, c);
     const bool vec_ok = (cols % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    {
+        // channel rows in shared memory when they fit (see query_group_smem_kernel)
+        constexpr int CHS = 2;
+        const size_t smem = (size_t)n * 4 * CHS;
+        static const bool off = [] { const char *e = getenv("PDM_QG_SMEM"); return e && e[0] == 'o'; }();   // A/B knob
+        if (!off && vec_ok && c >= 8 && cols >= 4096 && smem <= 64 * 1024 && cols < 0x7fffffffu) {
+            auto kern = query_group_smem_kernel<CHS>;
+            if (int rc = ensure_dynamic_smem((const void *)kern, smem)) return rc;
+            dim3 grid((c + CHS - 1) / CHS, b);
+            kern<<<grid, 512, smem, st>>>(c, n, (int)cols, 1, 0, nullptr, nullptr, points, idx, out);
+            count_launch();
+            PDM_CHECK_LAUNCH(what);
+            return PDM_OK;
+        }
+    }
     if (vec_ok) {
         const int cols4 = (int)(cols / 4);
         dim3 grid((cols4 + 255) / 256, chunks, b);

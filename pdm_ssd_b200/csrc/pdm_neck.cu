@@ -384,13 +384,12 @@ constexpr int kDenseCB = 32;
 
 template <bool VEC>
 __global__ void __launch_bounds__(256)
-pdm_dense_kernel(int c_total, int plane /*Y*X*/, long long nthreads, const int *__restrict__ pslot,
+pdm_dense_kernel(int c_total, int plane /*Y*X*/, const int *__restrict__ pslot,
                  const float *__restrict__ pf, float *__restrict__ bev) {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nthreads) return;
-    const int cblocks = (c_total + kDenseCB - 1) / kDenseCB;
-    const int j = (int)(t % plane);
-    const int cb = (int)((t / plane) % cblocks) * kDenseCB, b = (int)(t / ((long long)plane * cblocks));
+    // grid = (pillar blocks, channel blocks, frames): no index arithmetic beyond one multiply-add
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= plane) return;
+    const int cb = blockIdx.y * kDenseCB, b = blockIdx.z;
     const int cn = min(kDenseCB, c_total - cb);
     const int sl = __ldg(pslot + (size_t)b * plane + j);
     float v[kDenseCB];
@@ -445,6 +444,7 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
     if (cells_per_frame * (long long)(batch > 0 ? batch : 1) >= 0x7fffffffLL)
         return fail(PDM_ERR_UNSUPPORTED, "neck_forward: B*X*Y*Z must fit int32");
     if (batch == 0 || c == 0) return PDM_OK;
+    if (batch > 65535) return fail(PDM_ERR_UNSUPPORTED, "neck_forward: batch > 65535");
     if (!spatial_features || (p > 0 && (!point_coords || !point_features || !coef)))
         return fail(PDM_ERR_INVALID_ARG, "neck_forward: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
@@ -525,10 +525,10 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
     }
     if (err == cudaSuccess) {
         const int plane = grid[0] * grid[1], cblocks = (c + kDenseCB - 1) / kDenseCB;
-        const long long nthreads = (long long)batch * cblocks * plane;
-        const unsigned gx = (unsigned)((nthreads + 255) / 256);
-        if ((c % 4) == 0) pdm_dense_kernel<true><<<gx, 256, 0, st>>>(c, plane, nthreads, pslot, pf, spatial_features);
-        else pdm_dense_kernel<false><<<gx, 256, 0, st>>>(c, plane, nthreads, pslot, pf, spatial_features);
+        if (cblocks > 65535) return fail(PDM_ERR_UNSUPPORTED, "neck_forward: too many channels %d", c);
+        dim3 g((plane + 255) / 256, cblocks, batch);
+        if ((c % 4) == 0) pdm_dense_kernel<true><<<g, 256, 0, st>>>(c, plane, pslot, pf, spatial_features);
+        else pdm_dense_kernel<false><<<g, 256, 0, st>>>(c, plane, pslot, pf, spatial_features);
         count_launch();
         err = cudaGetLastError();
     }
