@@ -226,6 +226,80 @@ bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQ
 // ---------------------------------------------------------------------------------------
 // grid query: one warp per centre
 // ---------------------------------------------------------------------------------------
+// Crowded centre, one warp: bit k of a per-warp bitmap in shared memory for every hit, read back in
+// index order ("first nsample hits in ascending k" whatever order the candidates were visited in).
+// Lanes 0..8 pass the candidate range [rs, re) of their (dx,dy) column; the nine ranges are walked as
+// one flat index space.  bm: this warp's bitmap area, 32 * ((1 << wpl_log2) | 1) words.
+__device__ __forceinline__ void bq_warp_bitmap_pass(int lane, int rs, int re, float qx, float qy, float qz,
+                                                    float radius2, int nsample, int wpl_log2, unsigned *bm,
+                                                    const float4 *__restrict__ srt, int *__restrict__ row) {
+    const int wpl = 1 << wpl_log2;
+    const int stride = wpl | 1;  // odd stride: lane-contiguous ownership without bank conflicts
+    unsigned *mine = bm + lane * stride;  // words [lane*wpl, lane*wpl + wpl) of the frame's bitmap
+    int pre = lane < 9 ? re - rs : 0;  // lengths -> inclusive prefix over lanes 0..8
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, pre, o);
+        if (lane >= o) pre += y;
+    }
+    const int total_cand = __shfl_sync(kFullMask, pre, 8);
+    int pstart[9], rstart[9];   // exclusive prefix and first record of every range
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+        pstart[r] = r == 0 ? 0 : __shfl_sync(kFullMask, pre, r - 1);
+        rstart[r] = __shfl_sync(kFullMask, rs, r);
+    }
+    auto record_of = [&](int f) -> int {   // flat candidate number -> position in the sorted records
+        int i = rstart[0] + f;
+#pragma unroll
+        for (int r = 1; r < 9; ++r) i = f >= pstart[r] ? rstart[r] + (f - pstart[r]) : i;
+        return i;
+    };
+    __syncwarp();
+
+    __syncwarp();
+    for (int j = 0; j < wpl; ++j) mine[j] = 0u;
+    __syncwarp();
+    for (int f = lane; f < total_cand; f += 32) {
+        const float4 pt = __ldg(srt + record_of(f));
+        const float d2 = sqdist_ref(__fsub_rn(qx, pt.x), __fsub_rn(qy, pt.y), __fsub_rn(qz, pt.z));
+        if (d2 < radius2) {
+            const unsigned k = (unsigned)__float_as_int(pt.w);
+            const unsigned word = k >> 5;
+            atomicOr(&bm[(word >> wpl_log2) * stride + (word & (wpl - 1))], 1u << (k & 31u));
+        }
+    }
+    __syncwarp();
+    // (cnt > 32 >= ... the row is filled completely when nsample <= cnt; pad otherwise)
+    int c = 0;
+    for (int j = 0; j < wpl; ++j) c += __popc(mine[j]);
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int total = __shfl_sync(kFullMask, incl, 31);
+    int pos = incl - c;
+    int first = 0x7fffffff;
+    if (c > 0 && (pos < nsample || pos == 0)) {
+        for (int j = 0; j < wpl && pos < nsample; ++j) {
+            unsigned bits = mine[j];
+            while (bits && pos < nsample) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const int k = ((lane * wpl + j) << 5) + b;
+                if (first == 0x7fffffff) first = k;
+                row[pos++] = k;
+            }
+        }
+    }
+    if (total < nsample) {  // pad with the first (smallest) hit
+        const int f = __reduce_min_sync(kFullMask, first);
+        for (int l = total + lane; l < nsample; l += 32) row[l] = f;
+    }
+}
+
 constexpr int kQueryWarps = 8;
 
 __global__ void __launch_bounds__(kQueryWarps * 32)
@@ -325,47 +399,137 @@ bq_query_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2
         return;
     }
 
-    // Pass 2 -- crowded centre: bit k of a per-warp bitmap for every hit, read back in index order
-    __syncwarp();
-    for (int j = 0; j < wpl; ++j) mine[j] = 0u;
-    __syncwarp();
-    for (int f = lane; f < total_cand; f += 32) {
-        const float4 pt = __ldg(srt + record_of(f));
-        const float d2 = sqdist_ref(__fsub_rn(qx, pt.x), __fsub_rn(qy, pt.y), __fsub_rn(qz, pt.z));
-        if (d2 < radius2) {
-            const unsigned k = (unsigned)__float_as_int(pt.w);
-            const unsigned word = k >> 5;
-            atomicOr(&bm[(word >> wpl_log2) * stride + (word & (wpl - 1))], 1u << (k & 31u));
-        }
-    }
-    __syncwarp();
-    // (cnt > 32 >= ... the row is filled completely when nsample <= cnt; pad otherwise)
-    int c = 0;
-    for (int j = 0; j < wpl; ++j) c += __popc(mine[j]);
-    int incl = c;
+    // Pass 2 -- crowded centre: bitmap pass (shared with the thread-per-centre kernel)
+    bq_warp_bitmap_pass(lane, rs, re, qx, qy, qz, radius2, nsample, wpl_log2, bm, srt, row);
+}
+
+// ---------------------------------------------------------------------------------------
+// grid query: one THREAD per centre, crowded centres finished by the warp
+// ---------------------------------------------------------------------------------------
+// (Opt-in experiment, see ball_query_grid.)  The warp-per-centre kernel above spends ~900 warp instructions on a centre (prefix sums, flat
+// candidate walk, sort network -- executed by 32 lanes for ~40 candidates and ~9 hits) and is bound
+// by instruction issue (ncu: 78 % of the issue slots).  Here a thread walks the nine candidate
+// ranges of its own centre (ranges kept in shared memory, records read 16 bytes at a time; a lane's
+// consecutive records share cache lines) and appends the hits to a 32-entry list in shared memory;
+// 87 % of KITTI-shaped SA1 centres have at most 32 hits, which is then the complete hit set: an
+// insertion sort puts it in ascending index order and the warp writes the rows of its 32 centres
+// with coalesced 128-byte stores.  A centre with more than 32 hits stops scanning and is finished
+// by its whole warp with the bitmap pass.  Same results by construction: identical distance
+// arithmetic, "the nsample smallest hit indices in ascending order, padded with the first".
+constexpr int kTpcThreads = 128;
+constexpr int kTpcList = 32;
+constexpr int kTpcStride = kTpcThreads + 1;   // odd row stride: per-thread and per-warp accesses both conflict-free
+
+__global__ void __launch_bounds__(kTpcThreads)
+bq_query_tpc_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2,
+                    const float *__restrict__ new_xyz, const BQGrid *__restrict__ grids,
+                    const int *__restrict__ cellend, const float4 *__restrict__ sorted,
+                    int *__restrict__ idx) {
+    extern __shared__ unsigned tpc_smem[];
+    int *list = reinterpret_cast<int *>(tpc_smem);              // [kTpcList][kTpcStride]
+    int *rs_s = list + kTpcList * kTpcStride;                    // [9][kTpcStride]
+    int *re_s = rs_s + 9 * kTpcStride;                           // [9][kTpcStride]
+    unsigned *bitmap_all = reinterpret_cast<unsigned *>(re_s + 9 * kTpcStride);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int bi = blockIdx.y;
+    const int qi = blockIdx.x * kTpcThreads + tid;
+    const bool live = qi < m;
+    const BQGrid G = grids[bi];
+    const float *q = new_xyz + ((size_t)bi * m + (live ? qi : 0)) * 3;
+    const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
+    const int cx = bq_cell_coord(qx, G.ox, G.ix, G.gx);
+    const int cy = bq_cell_coord(qy, G.oy, G.iy, G.gy);
+    const int cz = bq_cell_coord(qz, G.oz, G.iz, G.gz);
+    const int *cend = cellend + (size_t)bi * cmax;
+    const float4 *srt = sorted + (size_t)bi * n;
+    const int z0 = max(cz - 1, 0), z1 = min(cz + 1, G.gz - 1);
+
+    // candidate ranges of the 3x3 columns (z0..z1 is contiguous in the cell order)
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(kFullMask, incl, o);
-        if (lane >= o) incl += y;
+    for (int r = 0; r < 9; ++r) {
+        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
+        int s = 0, e = 0;
+        if (live && x >= 0 && x < G.gx && y >= 0 && y < G.gy) {
+            const int c0 = (x * G.gy + y) * G.gz + z0, c1 = (x * G.gy + y) * G.gz + z1;
+            s = c0 == 0 ? 0 : __ldg(cend + c0 - 1);
+            e = __ldg(cend + c1);
+        }
+        rs_s[r * kTpcStride + tid] = s;
+        re_s[r * kTpcStride + tid] = e;
     }
-    const int total = __shfl_sync(kFullMask, incl, 31);
-    int pos = incl - c;
-    int first = 0x7fffffff;
-    if (c > 0 && (pos < nsample || pos == 0)) {
-        for (int j = 0; j < wpl && pos < nsample; ++j) {
-            unsigned bits = mine[j];
-            while (bits && pos < nsample) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1u;
-                const int k = ((lane * wpl + j) << 5) + b;
-                if (first == 0x7fffffff) first = k;
-                row[pos++] = k;
+    int cnt = 0;
+    {
+        // four records in flight per thread: the walk is a chain of dependent L2 reads otherwise
+        constexpr int PF = 4;
+        int r = 0, i = rs_s[tid], end = re_s[tid];
+        bool more = true;
+        while (more) {
+            int ii[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                while (i >= end && r < 8) {
+                    ++r;
+                    i = rs_s[r * kTpcStride + tid];
+                    end = re_s[r * kTpcStride + tid];
+                }
+                ii[u] = i < end ? i++ : -1;
             }
+            if (ii[0] < 0) break;
+            float4 pt[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) pt[u] = __ldg(srt + max(ii[u], 0));
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const float d2 = sqdist_ref(__fsub_rn(qx, pt[u].x), __fsub_rn(qy, pt[u].y), __fsub_rn(qz, pt[u].z));
+                if (ii[u] >= 0 && d2 < radius2 && cnt <= kTpcList) {
+                    if (cnt < kTpcList) list[cnt * kTpcStride + tid] = __float_as_int(pt[u].w);
+                    ++cnt;
+                }
+            }
+            more = ii[PF - 1] >= 0 && cnt <= kTpcList;   // crowded (> 32 hits): the warp takes over below
         }
     }
-    if (total < nsample) {  // pad with the first (smallest) hit
-        const int f = __reduce_min_sync(kFullMask, first);
-        for (int l = total + lane; l < nsample; l += 32) row[l] = f;
+    const bool crowded = cnt > kTpcList;
+    if (!crowded) {   // insertion sort of my hit list (ascending point index)
+        for (int a = 1; a < cnt; ++a) {
+            const int v = list[a * kTpcStride + tid];
+            int b = a - 1;
+            while (b >= 0) {
+                const int u = list[b * kTpcStride + tid];
+                if (u <= v) break;
+                list[(b + 1) * kTpcStride + tid] = u;
+                --b;
+            }
+            list[(b + 1) * kTpcStride + tid] = v;
+        }
+    }
+    __syncwarp();
+    const int wbase = tid - lane;                 // first thread of my warp
+    int *rows = idx + ((size_t)bi * m + (qi - lane)) * nsample;   // row of lane 0's centre
+    // rows of the complete lists: one coalesced store per 32 slots
+    unsigned wmask = __ballot_sync(kFullMask, live && !crowded && cnt > 0);
+    while (wmask) {
+        const int c = __ffs(wmask) - 1;
+        wmask &= wmask - 1u;
+        const int cc = __shfl_sync(kFullMask, cnt, c);
+        const int first = list[wbase + c];
+        const int v = lane < cc ? list[lane * kTpcStride + wbase + c] : first;
+        int *row = rows + (size_t)c * nsample;
+        for (int l = lane; l < nsample; l += 32) row[l] = l < cc ? v : first;   // l < cc implies l == lane
+    }
+    // crowded centres: bitmap pass by the whole warp
+    unsigned cmask = __ballot_sync(kFullMask, live && crowded);
+    if (cmask) {
+        unsigned *bm = bitmap_all + (size_t)w * 32 * ((1 << wpl_log2) | 1);
+        while (cmask) {
+            const int c = __ffs(cmask) - 1;
+            cmask &= cmask - 1u;
+            const float cqx = __shfl_sync(kFullMask, qx, c), cqy = __shfl_sync(kFullMask, qy, c), cqz = __shfl_sync(kFullMask, qz, c);
+            const int rs = lane < 9 ? rs_s[lane * kTpcStride + wbase + c] : 0;
+            const int re = lane < 9 ? re_s[lane * kTpcStride + wbase + c] : 0;
+            bq_warp_bitmap_pass(lane, rs, re, cqx, cqy, cqz, radius2, nsample, wpl_log2, bm, srt, rows + (size_t)c * nsample);
+            __syncwarp();
+        }
     }
 }
 
@@ -398,9 +562,23 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     count_launch();
     cudaError_t e1 = cudaGetLastError();
     if (e1 == cudaSuccess) {
-        if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK)
-            return PDM_ERR_UNSUPPORTED;  // message already recorded; caller falls back to the tiled kernel
-        {
+        // thread-per-centre kernel: opt-in (PDM_BQ_KERNEL=thread).  Measured on B200 (SA1, batch 16): 386 us
+        // alone vs 181 us for the warp-per-centre kernel (a thread's walk is a chain of dependent L2 reads
+        // and every warp serialises the bitmap passes of its ~4 crowded centres); the pipelined chain runs
+        // at the same rate with either (44.3k vs 45.7k frames/s), so the warp kernel stays the default.
+        static const bool warp_kernel = [] { const char *e = getenv("PDM_BQ_KERNEL"); return !(e && e[0] == 't' && e[1] == 'h'); }();
+        const size_t smem_tpc = (size_t)(kTpcList + 18) * kTpcStride * sizeof(int) +
+                                (size_t)(kTpcThreads / 32) * 32 * (wpl | 1) * sizeof(unsigned);
+        if (!warp_kernel && smem_tpc <= 100 * 1024 &&
+            ensure_dynamic_smem((const void *)bq_query_tpc_kernel, smem_tpc) == PDM_OK) {
+            dim3 grid((m + kTpcThreads - 1) / kTpcThreads, b);
+            bq_query_tpc_kernel<<<grid, kTpcThreads, smem_tpc, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
+                                                                    grids, cend, sorted, idx);
+            count_launch();
+            e1 = cudaGetLastError();
+        } else {
+            if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK)
+                return PDM_ERR_UNSUPPORTED;  // message already recorded; caller falls back to the tiled kernel
             dim3 grid((m + kQueryWarps - 1) / kQueryWarps, b);
             bq_query_kernel<<<grid, kQueryWarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
                                                                  grids, cend, sorted, idx);
@@ -423,8 +601,8 @@ extern "C" int pdm_ball_query(int b, int n, int m, float radius, int nsample, co
     if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "ball_query: batch %d > 65535", b);
     const float radius2 = radius * radius;  // fp32, as ball_query_gpu.cu:29
     cudaStream_t st = (cudaStream_t)stream;
-    const char *force = getenv("PDM_BQ_KERNEL");  // "tiled" | unset (debug/testing knob)
-    const bool tiled = force && force[0] == 't';
+    const char *force = getenv("PDM_BQ_KERNEL");  // "tiled" | "thread" | unset (debug/testing knob)
+    const bool tiled = force && force[0] == 't' && force[1] == 'i';
     // the grid needs a usable radius; NaN / non-positive radii have no hits at all or are
     // handled by the scan kernel with the reference's exact comparison
     if (!tiled && radius > 0.f && radius < INFINITY) {

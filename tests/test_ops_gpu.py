@@ -139,6 +139,30 @@ def test_ball_query_golden(path):
     assert np.array_equal(got, g["idx"]), os.path.basename(path)
 
 
+def test_ball_query_alternative_kernels_agree():
+    """The opt-in kernels (PDM_BQ_KERNEL=thread: thread per centre + warp bitmap pass for crowded centres;
+    =tiled: reference-shaped scan) give the same rows as the default one.  The knob is read once per
+    process, so each variant runs in its own interpreter."""
+    import subprocess, sys
+    code = (
+        "import numpy as np, torch, sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+        "import oracle; from pdm_ssd_b200 import pointnet2_utils as pu, synthetic;"
+        "ok = True\n"
+        "for n, m, r, s in [(16384, 4096, 0.8, 32), (4096, 1024, 1.6, 16), (1000, 37, 2.5, 64)]:\n"
+        "    fr = synthetic.kitti_batch(2, n, first_frame=3)[..., :3].copy()\n"
+        "    c = oracle.fps(fr, m)\n"
+        "    q = np.take_along_axis(fr, c[..., None].astype(np.int64).repeat(3, -1), 1)\n"
+        "    got = pu.ball_query(r, s, torch.from_numpy(fr).cuda(), torch.from_numpy(q).cuda()).cpu().numpy()\n"
+        "    ok = ok and np.array_equal(got, oracle.ball_query(r, s, fr, q))\n"
+        "print('AGREE' if ok else 'DIFFER')"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    for variant in ("thread", "tiled"):
+        env = dict(os.environ, PDM_BQ_KERNEL=variant)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "AGREE" in out.stdout, (variant, out.stdout[-500:])
+
+
 @pytest.mark.parametrize("n,m,r,s", [(4096, 1024, 0.8, 32), (4096, 1024, 1.6, 16), (1000, 37, 2.5, 64),
                                      (16384, 4096, 0.8, 32), (300, 300, 0.05, 4), (129, 1, 100.0, 200)])
 def test_ball_query_vs_oracle(n, m, r, s):
