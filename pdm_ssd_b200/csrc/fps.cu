@@ -573,6 +573,10 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
             return launch_bucket<16, 32, 8, 544>(b, n, m, p, xyz, temp, idx, stats, st);
         return launch_cap<16384>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
     }
+    if (!generic && fps_cluster_supports(n)) {   // frames larger than one SM: a cluster of CTAs per frame
+        const int rc = fps_cluster_launch(b, n, m, p, xyz, temp, idx, st);
+        if (rc != PDM_ERR_UNSUPPORTED) return rc;
+    }
     fps_generic_kernel<1024><<<b, 1024, 0, st>>>(n, m, p, xyz, temp, idx);
     count_launch();
     PDM_CHECK_LAUNCH("farthest_point_sampling(generic)");

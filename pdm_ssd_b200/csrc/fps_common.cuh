@@ -89,4 +89,8 @@ struct FpsCurve {
 int fps_l2_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st);
 bool fps_l2_supports(int n);
 
+// fps_cluster.cu: one thread-block cluster per frame for 16384 < n <= 196608 (same convention).
+int fps_cluster_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, cudaStream_t st);
+bool fps_cluster_supports(int n);
+
 }  // namespace pdm

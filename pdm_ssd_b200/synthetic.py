@@ -16,9 +16,9 @@ KITTI_RANGE = np.array([0.0, -40.0, -3.0, 70.4, 40.0, 1.0], dtype=np.float32)
 _CLASS_SIZES = np.array([[3.9, 1.6, 1.56], [0.8, 0.6, 1.73], [1.76, 0.6, 1.73]], dtype=np.float32)
 
 
-def _ring_scene(rng, n_az=1024):
+def _ring_scene(rng, n_az=1024, az_deg=(-45.0, 45.0)):
     elev = np.deg2rad(np.linspace(-24.8, 2.0, 64))
-    az = np.deg2rad(np.linspace(-45.0, 45.0, n_az))
+    az = np.deg2rad(np.linspace(az_deg[0], az_deg[1], n_az))
     e, a = np.meshgrid(elev, az, indexing="ij")
     e = e + rng.normal(0, 2e-4, e.shape)
     a = a + rng.normal(0, 2e-4, a.shape)
@@ -27,7 +27,7 @@ def _ring_scene(rng, n_az=1024):
         r_ground = np.where(e < -1e-3, 1.73 / np.tan(-e), np.inf)
     # vertical back-drop (walls, vegetation) at a per-azimuth-sector distance
     sector = rng.uniform(15.0, 75.0, 32)
-    r_wall = sector[(np.arange(n_az) * 32 // n_az)][None, :] / np.maximum(np.cos(a), 0.2)
+    r_wall = sector[(np.arange(n_az) * 32 // n_az)][None, :] / (np.maximum(np.cos(a), 0.2) if az_deg[1] - az_deg[0] < 180.0 else 1.0)
     r_wall = r_wall + rng.normal(0, 0.15, r_wall.shape)
     r = np.minimum(r_ground, r_wall)
     r = r + rng.normal(0, 0.01, r.shape)
@@ -103,6 +103,27 @@ def kitti_frame(seed, num_points=16384, n_az=None):
 def kitti_batch(batch, num_points=16384, first_frame=0, n_az=None):
     """(B, num_points, 4) float32, frame i seeded with 1000 + first_frame + i."""
     return np.stack([kitti_frame(1000 + first_frame + i, num_points, n_az) for i in range(batch)], 0)
+
+
+WAYMO_RANGE = np.array([-75.2, -75.2, -2.0, 75.2, 75.2, 4.0], dtype=np.float32)
+
+
+def waymo_frame(seed, num_points=163840):
+    """BASELINE configs[4] shape: a 360-degree 64-beam sweep (~2600 azimuth steps) clipped to the 150 m
+    Waymo range of SURVEY.md section 8(d), 5 channels (x, y, z, intensity, elongation), then the same
+    `sample_points` step."""
+    rng = np.random.default_rng(seed)
+    n_az = int(rng.integers(2500, 3300))
+    pts = np.concatenate([_ring_scene(rng, n_az, (-180.0, 180.0)), _boxes(rng)], 0)
+    lo, hi = WAYMO_RANGE[:3], WAYMO_RANGE[3:]
+    pts = pts[((pts >= lo) & (pts < hi)).all(1)]
+    extra = rng.uniform(0.0, 1.0, (len(pts), 2))
+    frame = np.concatenate([pts, extra], 1).astype(np.float32)
+    return np.ascontiguousarray(sample_points(frame, num_points, rng))
+
+
+def waymo_batch(batch, num_points=163840, first_frame=0):
+    return np.stack([waymo_frame(3000 + first_frame + i, num_points) for i in range(batch)], 0)
 
 
 def uniform_batch(batch, num_points, first_frame=0, extent=(70.4, 80.0, 4.0)):
