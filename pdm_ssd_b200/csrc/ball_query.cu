@@ -310,7 +310,7 @@ bq_query_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2
     extern __shared__ unsigned bitmap_all[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int bi = blockIdx.y;
-    const int qi = blockIdx.x * kQueryWarps + w;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + w;   // 8 warps per CTA, fewer when the bitmaps of a large frame need the room
     if (qi >= m) return;  // whole warp
     const int wpl = 1 << wpl_log2;
     const int stride = wpl | 1;  // odd stride: lane-contiguous ownership without bank conflicts
@@ -542,7 +542,9 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     int wpl_log2 = 0;  // bitmap words per lane, rounded up to a power of two
     while ((32 << wpl_log2) < words) ++wpl_log2;
     const int wpl = 1 << wpl_log2;
-    const size_t smem = (size_t)kQueryWarps * 32 * (wpl | 1) * sizeof(unsigned);
+    int qwarps = kQueryWarps;     // a warp's bitmap has n bits: large frames get fewer warps per CTA
+    while (qwarps > 1 && (size_t)qwarps * 32 * (wpl | 1) * sizeof(unsigned) > 200 * 1024) qwarps >>= 1;
+    const size_t smem = (size_t)qwarps * 32 * (wpl | 1) * sizeof(unsigned);
     if (smem > 200 * 1024) return PDM_ERR_UNSUPPORTED;  // caller falls back to the tiled kernel
 
     const size_t sz_grid = ((sizeof(BQGrid) * b + 255) / 256) * 256;
@@ -579,8 +581,8 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
         } else {
             if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK)
                 return PDM_ERR_UNSUPPORTED;  // message already recorded; caller falls back to the tiled kernel
-            dim3 grid((m + kQueryWarps - 1) / kQueryWarps, b);
-            bq_query_kernel<<<grid, kQueryWarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
+            dim3 grid((m + qwarps - 1) / qwarps, b);
+            bq_query_kernel<<<grid, qwarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
                                                                  grids, cend, sorted, idx);
             count_launch();
             e1 = cudaGetLastError();

@@ -3,9 +3,9 @@
 //
 // The any-size kernel (fps_generic_kernel) gives a frame one CTA and walks all n points from L2 every
 // round: 163840 points = 160 per thread per round, 32 us per round, 534 ms for 16384 samples.  Here the
-// frame is cut into `cl` contiguous chunks, one per CTA of a cluster of up to 16 CTAs (16 SMs of one
+// frame is cut into `cl` contiguous chunks, one per CTA of a cluster of up to 16 CTAs (SMs of one
 // GPC); a CTA keeps its chunk's coordinates AND running minima in shared memory (16 B/point, up to
-// 12288 points) for the whole kernel, so a round touches no global memory at all:
+// 14336 points) for the whole kernel, so a round touches no global memory at all:
 //   1. every thread updates its <= 12 points against the last sample and keeps its best
 //      (value bits, tiekey) -- the reference's argmax with its tie-break (fps.cu header);
 //   2. warp argmax with two redux.sync, CTA argmax through 32 shared-memory slots;
@@ -15,6 +15,10 @@
 //   5. every warp reduces the `cl` candidates (two redux.sync): the next sample and its coordinates.
 // Exactly the reference's sequence of samples and its final `temp` (bit-exact, ties included).
 #include <cooperative_groups.h>
+#include <stdlib.h>
+
+#include <map>
+#include <mutex>
 
 #include "fps_common.cuh"
 
@@ -23,12 +27,12 @@ namespace cg = cooperative_groups;
 namespace pdm {
 
 constexpr int kClThreads = 1024;
-constexpr int kClMaxPPT = 12;      // points per thread: 12288 points = 192 KB of shared memory per CTA
 constexpr int kClMax = 16;
+constexpr int kClMaxChunk = 14336;  // points per CTA: 16 B each = 224 KB of the 227 KB of shared memory
 
 __global__ void __launch_bounds__(kClThreads, 1)
-fps_cluster_kernel(int n, int m, int p, int ppt, const float *__restrict__ xyz, float *__restrict__ temp,
-                   int *__restrict__ idxs) {
+fps_cluster_kernel(int n, int m, int p, int cap /*points per CTA, a multiple of 1024*/, const float *__restrict__ xyz,
+                   float *__restrict__ temp, int *__restrict__ idxs) {
     extern __shared__ __align__(16) float cl_smem[];
     __shared__ unsigned long long wbest[kClThreads / 32];
     __shared__ unsigned long long cand_key[2][kClMax];
@@ -39,14 +43,14 @@ fps_cluster_kernel(int n, int m, int p, int ppt, const float *__restrict__ xyz, 
     const int frame = blockIdx.x / cl;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bsmask = (1u << p) - 1u;
-    const int cap = kClThreads * ppt;
     float *sx = cl_smem, *sy = sx + cap, *sz = sy + cap, *st = sz + cap;
     const float *dataset = xyz + (size_t)frame * n * 3;
     float *tmp = temp + (size_t)frame * n;
     int *out = idxs + (size_t)frame * m;
-    const int chunk = (n + cl - 1) / cl;
+    const int chunk = cap;            // a multiple of 1024 (see step 1)
     const int k0 = rank * chunk;
     const int cnt = max(0, min(chunk, n - k0));
+    const int ppt = chunk / kClThreads;
 
     for (int i = tid; i < cnt; i += kClThreads) {
         sx[i] = __ldg(dataset + (size_t)(k0 + i) * 3 + 0);
@@ -59,9 +63,13 @@ fps_cluster_kernel(int n, int m, int p, int ppt, const float *__restrict__ xyz, 
     cluster.sync();   // every CTA of the cluster is resident before anyone writes into its shared memory
 
     for (int j = 1; j < m; ++j) {
-        // 1. my points against the last sample; best = largest value, smallest tiekey among equals
-        unsigned bvb = 0u, btk = kPadKey;
+        // 1. my points against the last sample.  Chunks start at multiples of the reference block size
+        //    (1024 for every n >= 1024), so a thread's points tid, tid + 1024, ... share the bit-reversed
+        //    part of the tiekey and come in ascending tiekey order: keeping the FIRST maximum (strict >) is
+        //    the reference's tie-break inside the thread -- its own strided scan does exactly this.
+        unsigned bvb = 0u;
         int bi = -1;
+#pragma unroll 2
         for (int q = 0; q < ppt; ++q) {
             const int i = tid + q * kClThreads;
             if (i < cnt) {
@@ -70,16 +78,12 @@ fps_cluster_kernel(int n, int m, int p, int ppt, const float *__restrict__ xyz, 
                 const float d2 = fminf(d, t);
                 if (d2 != t) st[i] = d2;
                 const unsigned ub = __float_as_uint(d2);
-                if (ub > bvb || bi < 0) {
-                    bvb = ub; bi = i; btk = kPadKey;          // tiekey computed lazily
-                } else if (ub == bvb) {
-                    if (btk == kPadKey) btk = fps_tiekey((unsigned)(k0 + bi), p, bsmask);
-                    const unsigned tk = fps_tiekey((unsigned)(k0 + i), p, bsmask);
-                    if (tk < btk) { btk = tk; bi = i; }
-                }
+                const bool better = ub > bvb || bi < 0;
+                bvb = better ? ub : bvb;
+                bi = better ? i : bi;
             }
         }
-        if (bi >= 0 && btk == kPadKey) btk = fps_tiekey((unsigned)(k0 + bi), p, bsmask);
+        const unsigned btk = bi >= 0 ? fps_tiekey((unsigned)(k0 + bi), p, bsmask) : kPadKey;
         // 2. warp, then CTA
         {
             const unsigned mx = __reduce_max_sync(kFull, bvb);
@@ -108,8 +112,11 @@ fps_cluster_kernel(int n, int m, int p, int ppt, const float *__restrict__ xyz, 
             }
         }
         // 4. one barrier per round: candidates of this round are visible, everyone is done with the
-        //    slots of the previous round's parity
-        cluster.sync();
+        //    slots of the previous round's parity.  Only the publishing warp needs release semantics
+        //    (cg::cluster_group::sync() makes all 32 warps execute the fence: 26 % of the samples in ncu).
+        if (warp == 0) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        else asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
         // 5. the sample: largest value, smallest tiekey
         {
             const unsigned long long ck = lane < cl ? cand_key[par][lane] : 0ull;
@@ -127,27 +134,68 @@ fps_cluster_kernel(int n, int m, int p, int ppt, const float *__restrict__ xyz, 
     cluster.sync();   // nobody exits while a peer may still address its shared memory
 }
 
-bool fps_cluster_supports(int n) { return n > 16384 && n <= kClMax * kClThreads * kClMaxPPT; }
+bool fps_cluster_supports(int n) { return n > 16384 && n <= kClMax * kClMaxChunk; }   // (n > 16384: p = 10)
+
+// Clusters of `cl` CTAs of this kernel the device can keep resident at once (a 16-CTA cluster needs a
+// GPC with 16 free SMs: 7 on this B200, so a batch of 8 frames would run in two waves).
+static int max_active_clusters(int cl, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<int, size_t>, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    auto key = std::make_pair(dev * 64 + cl, smem);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cl);
+    cfg.blockDim = dim3(kClThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int v = 0;
+    if (cudaOccupancyMaxActiveClusters(&v, (const void *)fps_cluster_kernel, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        v = 0;
+    }
+    cache[key] = v;
+    return v;
+}
 
 // Returns PDM_ERR_UNSUPPORTED (no error recorded) when the shape is out of range or the device cannot
 // co-schedule a cluster of the needed size; the caller then uses the any-size kernel.
 int fps_cluster_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, cudaStream_t st) {
     if (!fps_cluster_supports(n)) return PDM_ERR_UNSUPPORTED;
-    int cl = 4;
-    while (cl < kClMax && (long long)cl * kClThreads * kClMaxPPT < n) cl <<= 1;
-    // more CTAs per frame while the batch leaves SMs idle and a thread keeps >= 4 points
-    while (cl < kClMax && (long long)b * cl * 2 <= kNumSMs && n / (cl * 2 * kClThreads) >= 4) cl <<= 1;
-    const int chunk = (n + cl - 1) / cl;
-    const int ppt = (chunk + kClThreads - 1) / kClThreads;
-    const size_t smem = (size_t)kClThreads * ppt * 16;
     auto kern = fps_cluster_kernel;
-    if (int rc = ensure_dynamic_smem((const void *)kern, smem)) return rc;
-    if (cl > 8) {
-        static std::atomic<int> allowed{0};   // 0 unknown, 1 ok, -1 refused
+    {
+        static std::atomic<int> allowed{0};   // clusters of more than 8 CTAs: 0 unknown, 1 ok, -1 refused
         if (allowed.load() == 0)
             allowed.store(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 1 : -1);
         if (allowed.load() < 0) { (void)cudaGetLastError(); return PDM_ERR_UNSUPPORTED; }
     }
+    if (int rc = ensure_dynamic_smem((const void *)kern, (size_t)kClMaxChunk * 16)) return rc;
+    // cluster size: the one with the least modelled time  waves(b, cl) x (1.0 + 0.2 x points per thread) us per
+    // round (constants measured on B200: 2.95 us at 10 points per thread, 2.27 us at 6)
+    int cl = 0, cap = 0;
+    double best = 1e30;
+    for (int c = kClMax; c >= 2; --c) {
+        const int chunk = ((n + c - 1) / c + kClThreads - 1) / kClThreads * kClThreads;
+        if (chunk > kClMaxChunk) break;
+        if ((long long)(c - 1) * chunk >= n) continue;   // the last CTA would be empty: a smaller cluster does the same
+        const int act = max_active_clusters(c, (size_t)chunk * 16);
+        if (getenv("PDM_DEBUG_CLUSTER")) fprintf(stderr, "[pdm]   cluster of %d: %d points per CTA, %d active clusters\n", c, chunk, act);
+        if (act < 1) continue;
+        const int waves = (b + act - 1) / act;
+        const double t = waves * (1.0 + 0.2 * (chunk / kClThreads));
+        if (t < best) { best = t; cl = c; cap = chunk; }
+    }
+    if (cl == 0) return PDM_ERR_UNSUPPORTED;
+    const size_t smem = (size_t)cap * 16;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b * cl));
     cfg.blockDim = dim3(kClThreads);
@@ -160,12 +208,9 @@ int fps_cluster_launch(int b, int n, int m, int p, const float *xyz, float *temp
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    int max_clusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&max_clusters, (const void *)kern, &cfg) != cudaSuccess || max_clusters < 1) {
-        (void)cudaGetLastError();
-        return PDM_ERR_UNSUPPORTED;
-    }
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, n, m, p, ppt, xyz, temp, idx);
+    static const bool dbg = getenv("PDM_DEBUG_CLUSTER") != nullptr;
+    if (dbg) fprintf(stderr, "[pdm] fps cluster: b=%d n=%d cl=%d smem=%zu max_active_clusters=%d\n", b, n, cl, smem, max_active_clusters(cl, smem));
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, n, m, p, cap, xyz, temp, idx);
     if (e != cudaSuccess) return fail((int)e, "farthest_point_sampling(cluster of %d): %s", cl, cudaGetErrorString(e));
     count_launch();
     return PDM_OK;

@@ -348,6 +348,19 @@ def test_waymo_scale_frame():
     assert np.array_equal(our_bq(40.0, 64, xyz, new_xyz[:, :64]), oracle.ball_query(40.0, 64, xyz, new_xyz[:, :64]))
 
 
+@pytest.mark.parametrize("b,n,m", [(3, 50000, 300), (2, 16385, 200), (1, 196608, 64)])
+def test_fps_cluster_kernel_vs_oracle(b, n, m):
+    """Frames larger than one SM take the thread-block-cluster kernel (fps_cluster.cu): same samples and
+    same final scratch as the oracle, duplicates (= exact ties) included; batch > 1, chunk tails, and the
+    largest supported frame."""
+    rng = np.random.default_rng(n)
+    xyz = (rng.uniform(0, 1, (b, n, 3)) * np.array([150.4, 150.4, 6.0]) - np.array([75.2, 75.2, 2.0])).astype(np.float32)
+    xyz[:, n // 2: n // 2 + n // 4] = xyz[:, : n // 4]          # a quarter of the points are duplicates
+    want, want_t = oracle.fps(xyz, m, return_temp=True)
+    got, got_t = our_fps(xyz, m, return_temp=True)
+    assert np.array_equal(got, want) and np.array_equal(got_t, want_t)
+
+
 def test_ball_query_degenerate_inputs():
     rng = np.random.default_rng(4)
     # all points identical; radius larger than the scene; radius tiny; nsample > n; non-finite coordinates
