@@ -228,45 +228,29 @@ bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQ
 // ---------------------------------------------------------------------------------------
 // Crowded centre, one warp: bit k of a per-warp bitmap in shared memory for every hit, read back in
 // index order ("first nsample hits in ascending k" whatever order the candidates were visited in).
-// Lanes 0..8 pass the candidate range [rs, re) of their (dx,dy) column; the nine ranges are walked as
-// one flat index space.  bm: this warp's bitmap area, 32 * ((1 << wpl_log2) | 1) words.
+// Lanes 0..8 pass the candidate range [rs, re) of their (dx,dy) column.  bm: this warp's bitmap area, 32 * ((1 << wpl_log2) | 1) words.
 __device__ __forceinline__ void bq_warp_bitmap_pass(int lane, int rs, int re, float qx, float qy, float qz,
                                                     float radius2, int nsample, int wpl_log2, unsigned *bm,
                                                     const float4 *__restrict__ srt, int *__restrict__ row) {
     const int wpl = 1 << wpl_log2;
     const int stride = wpl | 1;  // odd stride: lane-contiguous ownership without bank conflicts
     unsigned *mine = bm + lane * stride;  // words [lane*wpl, lane*wpl + wpl) of the frame's bitmap
-    int pre = lane < 9 ? re - rs : 0;  // lengths -> inclusive prefix over lanes 0..8
-#pragma unroll
-    for (int o = 1; o < 16; o <<= 1) {
-        const int y = __shfl_up_sync(kFullMask, pre, o);
-        if (lane >= o) pre += y;
-    }
-    const int total_cand = __shfl_sync(kFullMask, pre, 8);
-    int pstart[9], rstart[9];   // exclusive prefix and first record of every range
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-        pstart[r] = r == 0 ? 0 : __shfl_sync(kFullMask, pre, r - 1);
-        rstart[r] = __shfl_sync(kFullMask, rs, r);
-    }
-    auto record_of = [&](int f) -> int {   // flat candidate number -> position in the sorted records
-        int i = rstart[0] + f;
-#pragma unroll
-        for (int r = 1; r < 9; ++r) i = f >= pstart[r] ? rstart[r] + (f - pstart[r]) : i;
-        return i;
-    };
-    __syncwarp();
-
     __syncwarp();
     for (int j = 0; j < wpl; ++j) mine[j] = 0u;
     __syncwarp();
-    for (int f = lane; f < total_cand; f += 32) {
-        const float4 pt = __ldg(srt + record_of(f));
-        const float d2 = sqdist_ref(__fsub_rn(qx, pt.x), __fsub_rn(qy, pt.y), __fsub_rn(qz, pt.z));
-        if (d2 < radius2) {
-            const unsigned k = (unsigned)__float_as_int(pt.w);
-            const unsigned word = k >> 5;
-            atomicOr(&bm[(word >> wpl_log2) * stride + (word & (wpl - 1))], 1u << (k & 31u));
+    // a crowded centre has long ranges: walk them one after the other, lanes striding inside a range
+    // (the flat index space of pass 1 costs ~110 instructions per 32 candidates in index arithmetic)
+#pragma unroll 1
+    for (int r = 0; r < 9; ++r) {
+        const int r0 = __shfl_sync(kFullMask, rs, r), r1 = __shfl_sync(kFullMask, re, r);
+        for (int i = r0 + lane; i < r1; i += 32) {
+            const float4 pt = __ldg(srt + i);
+            const float d2 = sqdist_ref(__fsub_rn(qx, pt.x), __fsub_rn(qy, pt.y), __fsub_rn(qz, pt.z));
+            if (d2 < radius2) {
+                const unsigned k = (unsigned)__float_as_int(pt.w);
+                const unsigned word = k >> 5;
+                atomicOr(&bm[(word >> wpl_log2) * stride + (word & (wpl - 1))], 1u << (k & 31u));
+            }
         }
     }
     __syncwarp();
@@ -385,9 +369,7 @@ bq_query_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2
     if (cnt <= 32) {
         __syncwarp();
         int v = lane < cnt ? (int)bm[lane] : 0x7fffffff;
-#pragma unroll
-        for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
+        for (int k = 2; (k >> 1) < cnt; k <<= 1) {   // only the stages a list of cnt needs (padding sorts last)
             for (int j = k >> 1; j > 0; j >>= 1) {
                 const int o = __shfl_xor_sync(kFullMask, v, j);
                 const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
