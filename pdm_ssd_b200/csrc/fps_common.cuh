@@ -82,6 +82,33 @@ struct FpsCurve {
         }
         return (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
     }
+    // 18-bit variant (9 bits per axis on the Hilbert curve, 6 per axis on the Morton curve): with a
+    // 14-bit point index it makes a 32-bit sort key.  Cells of ext/512 (16 cm on a KITTI frame) are far
+    // below the size of a 32-point bucket, so the bucket boxes are as tight as with the full code.
+    __device__ unsigned code18(const float *c) const {
+        if (planar) {
+            int iu = (int)((c[ax_u] - lo[ax_u]) * inv16), iv = (int)((c[ax_v] - lo[ax_v]) * inv16);  // NaN -> 0
+            unsigned x = (unsigned)max(0, min(65535, iu)) >> 7, y = (unsigned)max(0, min(65535, iv)) >> 7;
+            unsigned d = 0u;
+#pragma unroll
+            for (int sft = 8; sft >= 0; --sft) {
+                const unsigned rx = (x >> sft) & 1u, ry = (y >> sft) & 1u;
+                d = (d << 2) | ((3u * rx) ^ ry);
+                if (ry == 0u) {
+                    if (rx == 1u) { x = ~x; y = ~y; }
+                    const unsigned tswap = x; x = y; y = tswap;
+                }
+            }
+            return d;
+        }
+        unsigned q[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int qi = (int)((c[a] - lo[a]) * inv);  // NaN -> 0
+            q[a] = (unsigned)max(0, min(1023, qi)) >> 4;
+        }
+        return (expand10(q[0]) << 2) | (expand10(q[1]) << 1) | expand10(q[2]);
+    }
 };
 
 // fps_l2.cu: throughput-oriented variant (coordinates stay in L2, several frames per SM).
