@@ -14,7 +14,8 @@ stream) with STREAMS batches in flight: the steps go round-robin to STREAMS CUDA
 replaying a CUDA graph of one step (one batch keeps only ~16 of 148 SMs busy while it samples, so
 independent batches overlap; nothing is skipped, every step is the full chain on its own batch).
 `latency` is the same step on a single stream, eager launches.  `e2e` is the pipelined throughput
-through host pinned buffers with the H2D/D2H copies inside every step;
+through the host API (`HostSAChain`): pinned point clouds in, the chain's products out, the H2D/D2H
+copies inside every step (`e2e_full_io`: the same with every tensor of the chain crossing PCIe);
 `roofline` is for the dominant kernel (farthest point sampling, SA1); `cpu_baseline` is the CPU
 oracle (oracle/, a port of the reference kernels' semantics) on this box's host cores.
 
@@ -283,18 +284,30 @@ def main():
     fps_kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in fps_ev[2:]]))
 
     # ---- end to end: host pinned buffers in, host results out, copies inside every step ---------------
-    hpipe = PipelinedSAChain(BATCH, STREAMS, N_POINTS, device=dev, host=True, fps_mode=_lib.FPS_MODE_THROUGHPUT)
+    # "points": what a serving loop moves per batch (point clouds in, the chain's products out);
+    # "full": every tensor of the chain through the host every step (see HostSAChain)
     pinned = [(torch.from_numpy(f).pin_memory(), torch.from_numpy(g).pin_memory()) for f, g in host]
-    hpipe.capture(pinned)
-    pipelined(hpipe, STREAMS)
-    barrier()
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h0.record()
-    pipelined(hpipe, args.steps)
-    h1.record()
-    barrier()
-    checksum = int(sum(int(c.h_out[1]["fps_idx"].sum().item()) for c in hpipe.chains))  # reads the host copies
-    e2e_value = world * BATCH * args.steps / (reduce_max(h0.elapsed_time(h1)) * 1e-3)
+    e2e = {}
+    for io in ("points", "full"):
+        hpipe = PipelinedSAChain(BATCH, STREAMS, N_POINTS, device=dev, host=True, fps_mode=_lib.FPS_MODE_THROUGHPUT, host_io=io)
+        hpipe.capture(pinned)
+        pipelined(hpipe, STREAMS)
+        barrier()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        pipelined(hpipe, args.steps)
+        h1.record()
+        barrier()
+        checksum = int(sum(int(c.h_out[1]["fps_idx"].sum().item()) for c in hpipe.chains))  # reads the host copies
+        e2e[io] = {"value": world * BATCH * args.steps / (reduce_max(h0.elapsed_time(h1)) * 1e-3), "unit": "frames/s",
+                   "h2d_bytes_per_step": hpipe.h2d_bytes, "d2h_bytes_per_step": hpipe.d2h_bytes, "checksum": checksum,
+                   "streams": STREAMS}
+        del hpipe
+        torch.cuda.empty_cache()
+    e2e["points"]["what"] = ("pinned host point clouds (B,N,4) in, sampled indices + centres of both layers and the final layer's "
+                             "ball-query indices out, copies inside every step; the SA2 feature tensor stands for SA1's MLP output "
+                             "and stays on the device")
+    e2e["full"]["what"] = "every tensor of the chain through the host every step: points + SA2 feature tensor in, indices/centres/ball indices of both layers out"
     clocks = sampler.summary() if rank == 0 else None
 
     if rank != 0:
@@ -333,8 +346,7 @@ def main():
         "chain_hbm": {"algorithmic_bytes_per_frame": ab["total"], "achieved_gbs": chain_gbs, "frac": chain_gbs / peak},
         "latency": {"ms_per_step_single_stream": latency_ms, "frames_per_s_single_stream": world * BATCH / (latency_ms * 1e-3),
                     "what": "same step, one stream, eager launches (no graphs, no overlap between batches)"},
-        "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": hpipe.h2d_bytes,
-                "d2h_bytes_per_step": hpipe.d2h_bytes, "checksum": checksum, "streams": STREAMS},
+        "e2e": e2e["points"], "e2e_full_io": e2e["full"],
         "gpu_launches": int(launches), "clocks": clocks,
     }
 

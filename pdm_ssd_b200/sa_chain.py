@@ -100,26 +100,40 @@ class SAChain:
 class HostSAChain:
     """End-to-end form: host (pinned) buffers in, host results out; copies inside the call.
 
-    Inputs per step: points (B,N,4) [x,y,z,intensity] and the SA2 feature tensor (B,64,4096).
-    Result per step: per layer the sampled indices, centres and ball-query indices."""
+    `io="points"` (default) is what a serving loop moves per batch: the raw point clouds (B,N,4)
+    [x,y,z,intensity] go in -- in the detector they are the only host input (`load_data_to_gpu`,
+    pcdet/models/__init__.py:23-36); the SA2 feature tensor stands for the output of SA1's shared MLP,
+    which lives on the device, so it is uploaded once -- and the chain's products come out: sampled
+    indices and centres of both layers and the final layer's ball-query indices (SA1's ball-query
+    indices are an intermediate that grouping consumes on the device).
+    `io="full"` moves everything every step: points + the SA2 feature tensor (B,64,4096) in, sampled
+    indices, centres and ball-query indices of both layers out."""
 
-    def __init__(self, batch, n_points=16384, layers=KITTI_CHAIN, device="cuda:0", backend=None):
+    def __init__(self, batch, n_points=16384, layers=KITTI_CHAIN, device="cuda:0", backend=None, io="points"):
+        assert io in ("points", "full")
+        self.io = io
         self.chain = SAChain(batch, n_points, layers, device, backend)
         dev = self.chain.dev
         self.d_points = torch.empty((batch, n_points, 4), dtype=torch.float32, device=dev)
         self.d_xyz = torch.empty((batch, n_points, 3), dtype=torch.float32, device=dev)
         self.d_feat1 = torch.empty((batch, 1, n_points), dtype=torch.float32, device=dev)
         self.d_feat2 = torch.empty((batch, layers[1].channels, layers[0].npoint), dtype=torch.float32, device=dev)
+        self._feat2_from = None
         self.h_out = []
-        for ws in self.chain.ws:
-            self.h_out.append({k: torch.empty(ws[k].shape, dtype=ws[k].dtype).pin_memory()
-                               for k in ("fps_idx", "new_xyz", "ball_idx")})
-        self.h2d_bytes = self.d_points.numel() * 4 + self.d_feat2.numel() * 4
+        last = len(self.chain.ws) - 1
+        for li, ws in enumerate(self.chain.ws):
+            keys = ("fps_idx", "new_xyz", "ball_idx") if (io == "full" or li == last) else ("fps_idx", "new_xyz")
+            self.h_out.append({k: torch.empty(ws[k].shape, dtype=ws[k].dtype).pin_memory() for k in keys})
+        self.h2d_bytes = self.d_points.numel() * 4 + (self.d_feat2.numel() * 4 if io == "full" else 0)
         self.d2h_bytes = sum(t.numel() * t.element_size() for o in self.h_out for t in o.values())
 
     def run(self, h_points: torch.Tensor, h_feat2: torch.Tensor):
         self.d_points.copy_(h_points, non_blocking=True)
-        self.d_feat2.copy_(h_feat2, non_blocking=True)
+        if self.io == "full":
+            self.d_feat2.copy_(h_feat2, non_blocking=True)
+        elif self._feat2_from is not h_feat2:      # device-resident stand-in for SA1's MLP output: uploaded once
+            self.d_feat2.copy_(h_feat2, non_blocking=True)
+            self._feat2_from = h_feat2
         self.d_xyz.copy_(self.d_points[..., :3])
         self.d_feat1.copy_(self.d_points[..., 3:].transpose(1, 2))
         ws = self.chain.run(self.d_xyz, (self.d_feat1, self.d_feat2))
@@ -146,13 +160,15 @@ class PipelinedSAChain:
     frames per SM) gives more frames/s at a longer per-batch latency; results are bit-identical."""
 
     def __init__(self, batch, n_streams=4, n_points=16384, layers=KITTI_CHAIN, device="cuda:0", host=False, backend=None,
-                 fps_mode=None):
+                 fps_mode=None, host_io="points"):
         self.dev = torch.device(device)
         self.host = host
         self.fps_mode = fps_mode
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_streams)]
-        cls = HostSAChain if host else SAChain
-        self.chains = [cls(batch, n_points, layers, self.dev, backend) for _ in range(n_streams)]
+        if host:
+            self.chains = [HostSAChain(batch, n_points, layers, self.dev, backend, io=host_io) for _ in range(n_streams)]
+        else:
+            self.chains = [SAChain(batch, n_points, layers, self.dev, backend) for _ in range(n_streams)]
         self.graphs = None
         self.slot_args = None
         self.launches_per_step = None
