@@ -335,7 +335,8 @@ fps_l2_kernel(int n, int m, int p, const float *__restrict__ xyz, const float *_
             const int pos0 = j0 * (NW * 32) + wbase, pos1 = j1 * (NW * 32) + wbase;
             const float x0 = __ldg(gx + pos0), y0 = __ldg(gy + pos0), z0 = __ldg(gz + pos0);
             const float x1 = __ldg(gx + pos1), y1 = __ldg(gy + pos1), z1 = __ldg(gz + pos1);
-            float n0 = ts[pos0], n1 = ts[pos1];
+            const float o0 = ts[pos0], o1 = ts[pos1];
+            float n0 = o0, n1 = o1;
             unsigned s0 = __shfl_sync(kFull, amask, j0), s1 = __shfl_sync(kFull, amask, j1);
             while (s0) {
                 const int k = 31 - __clz(s0);
@@ -349,12 +350,16 @@ fps_l2_kernel(int n, int m, int p, const float *__restrict__ xyz, const float *_
                 const float4 c = ws[k];
                 n1 = fminf(sqdist_ref(__fsub_rn(x1, c.x), __fsub_rn(y1, c.y), __fsub_rn(z1, c.z)), n1);
             }
+            // the box test is conservative: a bucket can survive it without any of its points coming
+            // closer to a new sample -- then its summary is still valid and the reductions are skipped
+            const bool ch0 = __any_sync(kFull, n0 != o0), ch1 = two && __any_sync(kFull, n1 != o1);
+            if (!ch0 && !ch1) continue;
             const Upd u0 = finish(pos0, x0, y0, z0, n0);
             const Upd u1 = finish(pos1, x1, y1, z1, n1);   // (j1 == j0 when single: same result, harmless)
-            ts[pos0] = n0;
-            if (two) ts[pos1] = n1;
-            if (lane == j0) { bmax = u0.mx; bwl = u0.wl; bsec = u0.sec; bwx = u0.wx; bwy = u0.wy; bwz = u0.wz; }
-            if (two && lane == j1) { bmax = u1.mx; bwl = u1.wl; bsec = u1.sec; bwx = u1.wx; bwy = u1.wy; bwz = u1.wz; }
+            if (ch0) ts[pos0] = n0;
+            if (ch1) ts[pos1] = n1;
+            if (ch0 && lane == j0) { bmax = u0.mx; bwl = u0.wl; bsec = u0.sec; bwx = u0.wx; bwy = u0.wy; bwz = u0.wz; }
+            if (ch1 && lane == j1) { bmax = u1.mx; bwl = u1.wl; bsec = u1.sec; bwx = u1.wx; bwy = u1.wy; bwz = u1.wz; }
             dirty = true;
         }
         if (j >= m) break;
