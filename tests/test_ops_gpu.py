@@ -105,6 +105,73 @@ def test_fps_full_size_properties():
     assert np.array_equal(our_fps(frames[5:6], 4096)[0], idx[5])
 
 
+def test_chain_full_size_properties():
+    """BASELINE configs[1] at full size (16 x 16384 -> 4096 -> 1024, r = 0.8 / 1.6, 32 samples): properties
+    that do not need the oracle -- ball-query rows hold the SMALLEST hit indices in ascending order and are
+    padded with the first one, every listed neighbour is inside the ball and (away from the boundary) no
+    in-ball point with a smaller index is missing; grouping is an exact gather; a second run is identical;
+    the oracle itself on two frames."""
+    from pdm_ssd_b200.sa_chain import SAChain
+    frames = _t(synthetic.kitti_batch(16))
+    xyz = frames[..., :3].contiguous()
+    f1 = frames[..., 3:].transpose(1, 2).contiguous()
+    f2 = torch.randn(16, 64, 4096, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    chain = SAChain(16, 16384, device=DEV)
+    ws = chain.run(xyz, (f1, f2))
+    first = [{k: v.clone() for k, v in w.items() if torch.is_tensor(v)} for w in ws]
+    cur = xyz
+    for L, w, feat in zip(chain.layers, first, (f1, f2)):
+        idx, new_xyz, bq, grouped = w["fps_idx"].long(), w["new_xyz"], w["ball_idx"].long(), w["grouped"]
+        B, M, S = bq.shape
+        assert torch.equal(new_xyz, torch.gather(cur, 1, idx[..., None].expand(-1, -1, 3)))
+        # rows: strictly ascending up to the hit count, then copies of the first hit
+        rising = bq[:, :, 1:] > bq[:, :, :-1]
+        cnt = 1 + rising.long().cumprod(-1).sum(-1)                              # hits listed per row
+        pos = torch.arange(S, device=DEV)[None, None, :]
+        assert torch.equal(torch.where(pos < cnt[..., None], bq, bq[:, :, :1].expand(-1, -1, S)), bq)
+        # every listed neighbour is inside the ball (the centre itself is a point of the cloud: no empty rows)
+        nb = torch.gather(cur, 1, bq.reshape(B, -1)[..., None].expand(-1, -1, 3)).view(B, M, S, 3)
+        d2 = ((nb.double() - new_xyz[:, :, None, :].double()) ** 2).sum(-1)
+        r2 = float(np.float32(L.radius) * np.float32(L.radius))
+        assert bool((d2 < r2 * (1 + 1e-5)).all())
+        # completeness on a sample of centres: the in-ball points with the smallest indices are the row
+        for b in (0, 7, 15):
+            sel = torch.arange(0, M, 97, device=DEV)
+            dd = ((cur[b][None, :, :].double() - new_xyz[b, sel][:, None, :].double()) ** 2).sum(-1)   # (sel, N)
+            clear_in = dd < r2 * (1 - 1e-5)
+            for row, c in enumerate(sel.tolist()):
+                want = torch.nonzero(clear_in[row]).flatten()[:S]
+                got = bq[b, c, : int(cnt[b, c])]
+                # every clearly-inside point below the largest listed index is listed
+                lim = int(got[-1]) if int(cnt[b, c]) == S else cur.shape[1]
+                assert set(want[want <= lim].tolist()) <= set(got.tolist())
+        # grouping = exact gather of [xyz - centre, features]
+        C = feat.shape[1]
+        gx = nb.permute(0, 3, 1, 2) - new_xyz.transpose(1, 2)[..., None]
+        assert torch.equal(grouped[:, :3], gx)
+        gf = torch.gather(feat, 2, bq.reshape(B, 1, -1).expand(-1, C, -1)).view(B, C, M, S)
+        assert torch.equal(grouped[:, 3:], gf)
+        cur = new_xyz
+    # determinism: a second run (and one in throughput mode) gives identical tensors
+    ws2 = chain.run(xyz, (f1, f2))
+    for a, b_ in zip(first, ws2):
+        for k in ("fps_idx", "new_xyz", "ball_idx", "grouped"):
+            assert torch.equal(a[k], b_[k]), k
+    _lib.set_fps_mode(_lib.FPS_MODE_THROUGHPUT)
+    try:
+        ws3 = chain.run(xyz, (f1, f2))
+        for a, b_ in zip(first, ws3):
+            assert torch.equal(a["fps_idx"], b_["fps_idx"]) and torch.equal(a["ball_idx"], b_["ball_idx"])
+    finally:
+        _lib.set_fps_mode(_lib.FPS_MODE_AUTO)
+    # and the oracle on two frames
+    fr = xyz[:2].cpu().numpy()
+    fi = oracle.fps(fr, 4096)
+    assert np.array_equal(first[0]["fps_idx"][:2].cpu().numpy(), fi)
+    nx = np.take_along_axis(fr, fi[..., None].astype(np.int64).repeat(3, -1), 1)
+    assert np.array_equal(first[0]["ball_idx"][:2].cpu().numpy(), oracle.ball_query(0.8, 32, fr, nx))
+
+
 def test_fps_generic_kernel_matches(monkeypatch):
     xyz = synthetic.kitti_batch(2, 4096)[..., :3].copy()
     a = our_fps(xyz, 512)
