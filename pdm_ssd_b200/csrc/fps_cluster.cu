@@ -69,34 +69,18 @@ fps_cluster_kernel(int n, int m, int p, int cap /*points per CTA, a multiple of 
         //    the reference's tie-break inside the thread -- its own strided scan does exactly this.
         unsigned bvb = 0u;
         int bi = -1;
-        if (cnt == chunk) {   // every CTA but the last: no bounds checks, offsets known at compile time
-            const float *px = sx + tid, *py = sy + tid, *pz = sz + tid;
-            float *pt = st + tid;
-#pragma unroll 4
-            for (int q = 0; q < ppt; ++q) {
-                const int o = q * kClThreads;
-                const float d = sqdist_ref(__fsub_rn(px[o], x1), __fsub_rn(py[o], y1), __fsub_rn(pz[o], z1));
-                const float t = pt[o];
+#pragma unroll 2
+        for (int q = 0; q < ppt; ++q) {
+            const int i = tid + q * kClThreads;
+            if (i < cnt) {
+                const float d = sqdist_ref(__fsub_rn(sx[i], x1), __fsub_rn(sy[i], y1), __fsub_rn(sz[i], z1));
+                const float t = st[i];
                 const float d2 = fminf(d, t);
-                if (d2 != t) pt[o] = d2;
+                if (d2 != t) st[i] = d2;
                 const unsigned ub = __float_as_uint(d2);
-                const bool better = ub > bvb || q == 0;
+                const bool better = ub > bvb || bi < 0;
                 bvb = better ? ub : bvb;
-                bi = better ? tid + o : bi;
-            }
-        } else {
-            for (int q = 0; q < ppt; ++q) {
-                const int i = tid + q * kClThreads;
-                if (i < cnt) {
-                    const float d = sqdist_ref(__fsub_rn(sx[i], x1), __fsub_rn(sy[i], y1), __fsub_rn(sz[i], z1));
-                    const float t = st[i];
-                    const float d2 = fminf(d, t);
-                    if (d2 != t) st[i] = d2;
-                    const unsigned ub = __float_as_uint(d2);
-                    const bool better = ub > bvb || bi < 0;
-                    bvb = better ? ub : bvb;
-                    bi = better ? i : bi;
-                }
+                bi = better ? i : bi;
             }
         }
         const unsigned btk = bi >= 0 ? fps_tiekey((unsigned)(k0 + bi), p, bsmask) : kPadKey;
