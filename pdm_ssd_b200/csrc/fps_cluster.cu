@@ -159,6 +159,9 @@ static int max_active_clusters(int cl, size_t smem) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int v = 0;
+    // clusters of more than 8 CTAs are "non-portable": allowed per device, once (first query on that device)
+    if (cl > 8 && cudaFuncSetAttribute((const void *)fps_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+        (void)cudaGetLastError();
     if (cudaOccupancyMaxActiveClusters(&v, (const void *)fps_cluster_kernel, &cfg) != cudaSuccess) {
         (void)cudaGetLastError();
         v = 0;
@@ -172,12 +175,6 @@ static int max_active_clusters(int cl, size_t smem) {
 int fps_cluster_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, cudaStream_t st) {
     if (!fps_cluster_supports(n)) return PDM_ERR_UNSUPPORTED;
     auto kern = fps_cluster_kernel;
-    {
-        static std::atomic<int> allowed{0};   // clusters of more than 8 CTAs: 0 unknown, 1 ok, -1 refused
-        if (allowed.load() == 0)
-            allowed.store(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess ? 1 : -1);
-        if (allowed.load() < 0) { (void)cudaGetLastError(); return PDM_ERR_UNSUPPORTED; }
-    }
     if (int rc = ensure_dynamic_smem((const void *)kern, (size_t)kClMaxChunk * 16)) return rc;
     // cluster size: the one with the least modelled time  waves(b, cl) x (1.0 + 0.2 x points per thread) us per
     // round (constants measured on B200: 2.95 us at 10 points per thread, 2.27 us at 6)
