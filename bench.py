@@ -39,6 +39,9 @@ import numpy as np  # noqa: E402
 
 BATCH = 16
 N_POINTS = 16384
+METRIC = "frames/s (SA op chain, 16384-pt frames, batch 16 per GPU)"     # BASELINE.json metric, both arms
+WORKLOAD = ("configs[1]: pointnet2 SA op chain (FPS 16384->4096->1024, ball query r=0.8/1.6 x32, "
+            "xyz+feature grouping C=1/64), KITTI-shaped synthetic frames")
 STREAMS = int(os.environ.get("PDM_BENCH_STREAMS", "24"))  # batches in flight (one CUDA stream + graph + input batch + workspace each)
 
 
@@ -142,11 +145,11 @@ def run_reference_arm(args, rank, world):
     dt = time.perf_counter() - t0
     value = frames_per_step * args.steps / dt
     line = {
-        "impl": "reference", "metric": "frames/s (SA op chain, 16384-pt frames)", "value": value, "unit": "frames/s",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: pointnet2 SA op chain (FPS 16384->4096->1024, ball query r=0.8/1.6 x32, "
-                               "xyz+feature grouping), KITTI-shaped synthetic frames", "frames_per_step": frames_per_step},
+        "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "points_per_frame": N_POINTS,
+                   "frames_per_step": frames_per_step},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d frame(s) per step x %d steps, all ops of the chain on the CPU oracle" % (frames_per_step, args.steps)},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -327,11 +330,10 @@ def main():
             traffic = json.load(f).get("dram_bytes_per_launch")
     chain_gbs = ab["total"] * BATCH * args.steps / (ms_max * 1e-3) / 1e9
     line = {
-        "metric": "frames/s (SA op chain, 16384-pt frames, batch 16 per GPU)", "value": value, "unit": "frames/s",
+        "metric": METRIC, "value": value, "unit": "frames/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: pointnet2 SA op chain (FPS 16384->4096->1024, ball query r=0.8/1.6 x32, "
-                               "xyz+feature grouping C=1/64), KITTI-shaped synthetic frames",
+        "config": {"workload": WORKLOAD,
                    "batch_per_gpu": BATCH, "points_per_frame": N_POINTS,
                    "streams": STREAMS, "cuda_graphs": True,
                    "fps_mode": "throughput (fps_l2_kernel, 2 frames/SM) in the pipelined and e2e regions; latency pass: on-chip fps_bucket_kernel",
