@@ -243,11 +243,19 @@ __device__ __forceinline__ void bq_warp_bitmap_pass(int lane, int rs, int re, fl
 #pragma unroll 1
     for (int r = 0; r < 9; ++r) {
         const int r0 = __shfl_sync(kFullMask, rs, r), r1 = __shfl_sync(kFullMask, re, r);
-        for (int i = r0 + lane; i < r1; i += 32) {
-            const float4 pt = __ldg(srt + i);
-            const float d2 = sqdist_ref(__fsub_rn(qx, pt.x), __fsub_rn(qy, pt.y), __fsub_rn(qz, pt.z));
-            if (d2 < radius2) {
-                const unsigned k = (unsigned)__float_as_int(pt.w);
+        for (int i = r0 + lane; i < r1; i += 64) {   // two records in flight per lane (ncu: the distance
+            const bool two = i + 32 < r1;             // computation waited for its load: 20 % of the samples)
+            const float4 pa = __ldg(srt + i);
+            const float4 pb = __ldg(srt + (two ? i + 32 : i));
+            const float da = sqdist_ref(__fsub_rn(qx, pa.x), __fsub_rn(qy, pa.y), __fsub_rn(qz, pa.z));
+            const float db = sqdist_ref(__fsub_rn(qx, pb.x), __fsub_rn(qy, pb.y), __fsub_rn(qz, pb.z));
+            if (da < radius2) {
+                const unsigned k = (unsigned)__float_as_int(pa.w);
+                const unsigned word = k >> 5;
+                atomicOr(&bm[(word >> wpl_log2) * stride + (word & (wpl - 1))], 1u << (k & 31u));
+            }
+            if (two && db < radius2) {
+                const unsigned k = (unsigned)__float_as_int(pb.w);
                 const unsigned word = k >> 5;
                 atomicOr(&bm[(word >> wpl_log2) * stride + (word & (wpl - 1))], 1u << (k & 31u));
             }
