@@ -91,7 +91,7 @@ fps_generic_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__
 template <int NW, int BPW, int KMAX>
 struct FpsSmem {
     static constexpr int CAP = NW * BPW * 32;
-    // [0, 12*CAP): sx, sy, sz (aliased by the 8*CAP-byte sort keys during set-up), then
+    // [0, 12*CAP): sx, sy, sz (aliased by the 4*CAP-byte sort keys / exchange buffer during set-up), then
     // pub[2][2*NW] uint2 (value bits, position) -- two candidates per warp,
     // pubU[2][NW] bound on every other point of the warp, samp[NW][KMAX] float4 accepted samples
     // (one private copy per warp), frame-box scratch.
@@ -194,7 +194,6 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
     float *sx = reinterpret_cast<float *>(smem_raw);
     float *sy = sx + CAP;
     float *sz = sy + CAP;
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw);
     uint2 *pub = reinterpret_cast<uint2 *>(smem_raw + L::kPubOff);
     unsigned *pubU = reinterpret_cast<unsigned *>(smem_raw + L::kUOff);
     float4 *samp = reinterpret_cast<float4 *>(smem_raw + L::kSampOff);
@@ -242,32 +241,27 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
     FpsCurve curve;   // spatial sort code (fps_common.cuh)
     curve.init(lo, hi);
 
-    // ---- 2. keys -> shared, bitonic sort ---------------------------------------------------
-    for (int k = tid; k < CAP; k += T) {
-        unsigned long long key = ~0ull;
-        if (k < n) {
-            const float c[3] = {__ldg(dataset + k * 3 + 0), __ldg(dataset + k * 3 + 1), __ldg(dataset + k * 3 + 2)};
-            const unsigned code = curve.code(c);
-            key = ((unsigned long long)code << 32) | (unsigned)k;
+    // ---- 2. sort along the curve: 32-bit keys (18-bit code | 14-bit index), BPW per thread in registers
+    //         (fps_sort_keys: register / shuffle / a few shared-memory stages; the first version sorted
+    //         64-bit keys in shared memory with a barrier per stage: ~0.25 ms of a 2.3 ms kernel)
+    unsigned *skeys = reinterpret_cast<unsigned *>(smem_raw);
+    {
+        unsigned v[BPW];
+#pragma unroll
+        for (int r = 0; r < BPW; ++r) {
+            const int k = r * T + tid;            // any initial arrangement will do: coalesced reads
+            v[r] = 0xffffffffu;                   // padding sorts last
+            if (k < n) {
+                const float c[3] = {__ldg(dataset + k * 3 + 0), __ldg(dataset + k * 3 + 1), __ldg(dataset + k * 3 + 2)};
+                v[r] = (curve.code18(c) << 14) | (unsigned)k;
+            }
         }
-        keys[k] = key;
+        fps_sort_keys<BPW, T>(v, skeys, tid);
+        __syncthreads();                           // nobody is still reading the exchange buffer
+#pragma unroll
+        for (int r = 0; r < BPW; ++r) skeys[tid * BPW + r] = v[r];   // sorted position e = tid * BPW + r
     }
     __syncthreads();
-    for (int kk = 2; kk <= CAP; kk <<= 1) {
-        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-            for (int i = tid; i < CAP / 2; i += T) {
-                const int l = ((i & ~(jj - 1)) << 1) | (i & (jj - 1));
-                const int r = l | jj;
-                const unsigned long long a = keys[l], b = keys[r];
-                const bool up = (l & kk) == 0;
-                if ((a > b) == up) {
-                    keys[l] = b;
-                    keys[r] = a;
-                }
-            }
-            __syncthreads();
-        }
-    }
 
     // ---- 3. distribute: lane owns slot `lane` of buckets  b = j*NW + w --------------------
     // Sorted position pos = b*32 + lane.  Padding keys sort last, so pos >= n <=> padding.
@@ -276,7 +270,7 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
     float t[BPW];       // running min distance of my point in owned bucket j
     unsigned kk_[BPW];
 #pragma unroll
-    for (int j = 0; j < BPW; ++j) kk_[j] = (unsigned)keys[((j * NW + w) << 5) + lane];  // low word = k
+    for (int j = 0; j < BPW; ++j) kk_[j] = skeys[((j * NW + w) << 5) + lane] & 0x3fffu;   // low 14 bits = k
     __syncthreads();  // keys are dead from here on; the region becomes sx/sy/sz
 #pragma unroll
     for (int j = 0; j < BPW; ++j) {

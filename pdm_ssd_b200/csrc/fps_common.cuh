@@ -111,6 +111,73 @@ struct FpsCurve {
     }
 };
 
+// Bitonic sort of E * T 32-bit keys held E per thread in registers (element index e = tid * E + r), for a
+// CTA of T threads.  The compare-exchange distance j is handled where the partner lives:
+//   j < E          inside the thread (register pairs),
+//   E <= j < 32 E  in another lane of the warp (shfl.xor),
+//   j >= 32 E      in another warp: one transposed round trip through shared memory (conflict-free).
+// xch: E * T words of shared memory (only touched by the cross-warp stages).  All T threads must call.
+template <int E, int T>
+__device__ __forceinline__ void fps_sort_keys(unsigned (&v)[E], unsigned *xch, int tid) {
+    static_assert((E & (E - 1)) == 0 && E >= 2 && E <= 32, "keys per thread: a power of two");
+    // stages whose direction depends on the register index only
+#pragma unroll
+    for (int k = 2; k < E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                if ((r & j) == 0) {
+                    const unsigned a = v[r], b = v[r | j];
+                    const unsigned mn = min(a, b), mx = max(a, b);
+                    const bool asc = (r & k) == 0;
+                    v[r] = asc ? mn : mx;
+                    v[r | j] = asc ? mx : mn;
+                }
+            }
+        }
+    }
+    for (int k = E; k <= E * T; k <<= 1) {
+        const bool asc = ((tid * E) & k) == 0;     // the same for all registers of a thread
+        for (int j = k >> 1; j >= 32 * E; j >>= 1) {            // partner in another warp
+            const int pt = tid ^ (j / E);
+            const bool keep_min = asc == ((tid & (j / E)) == 0);
+#pragma unroll
+            for (int r = 0; r < E; ++r) xch[r * T + tid] = v[r];
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                const unsigned p = xch[r * T + pt];
+                v[r] = keep_min ? min(v[r], p) : max(v[r], p);
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int jl = 16; jl >= 1; jl >>= 1) {                  // partner in another lane: j = E * jl
+            if (E * jl < k) {
+                const bool keep_min = asc == ((tid & jl) == 0);
+#pragma unroll
+                for (int r = 0; r < E; ++r) {
+                    const unsigned p = __shfl_xor_sync(kFull, v[r], jl);
+                    v[r] = keep_min ? min(v[r], p) : max(v[r], p);
+                }
+            }
+        }
+#pragma unroll
+        for (int J = E >> 1; J >= 1; J >>= 1) {                 // partner in another register
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                if ((r & J) == 0) {
+                    const unsigned a = v[r], b = v[r | J];
+                    const unsigned mn = min(a, b), mx = max(a, b);
+                    v[r] = asc ? mn : mx;
+                    v[r | J] = asc ? mx : mn;
+                }
+            }
+        }
+    }
+}
+
 // fps_l2.cu: throughput-oriented variant (coordinates stay in L2, several frames per SM).
 // Returns PDM_ERR_UNSUPPORTED (without recording an error) when the shape is outside its range.
 int fps_l2_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st);

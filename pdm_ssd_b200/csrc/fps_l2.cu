@@ -93,68 +93,7 @@ fps_prepare_kernel(int n, const float *__restrict__ xyz, const float *__restrict
             v[r] = (curve.code18(c) << 14) | (unsigned)k;
         }
     }
-    // element index e = tid * 16 + r; ascending block iff (e & k) == 0; keep the minimum iff the element
-    // is the lower one of its pair in an ascending block (or the upper one in a descending block)
-    auto reg_stage = [&](auto jtag, bool asc) {
-        constexpr int J = decltype(jtag)::value;
-#pragma unroll
-        for (int r = 0; r < E; ++r) {
-            if ((r & J) == 0) {
-                const unsigned a = v[r], b = v[r | J];
-                const unsigned mn = min(a, b), mx = max(a, b);
-                v[r] = asc ? mn : mx;
-                v[r | J] = asc ? mx : mn;
-            }
-        }
-    };
-    // k = 2, 4, 8: direction depends on the register index only
-#pragma unroll
-    for (int k = 2; k <= 8; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (int r = 0; r < E; ++r) {
-                if ((r & j) == 0) {
-                    const unsigned a = v[r], b = v[r | j];
-                    const unsigned mn = min(a, b), mx = max(a, b);
-                    const bool asc = (r & k) == 0;
-                    v[r] = asc ? mn : mx;
-                    v[r | j] = asc ? mx : mn;
-                }
-            }
-        }
-    }
-    for (int k = 16; k <= CAP; k <<= 1) {
-        const bool asc = ((tid * E) & k) == 0;     // the same for all 16 registers of a thread
-        for (int j = k >> 1; j >= 16 * 32; j >>= 1) {          // partner in another warp
-            const int pt = tid ^ (j >> 4);
-            const bool keep_min = asc == ((tid & (j >> 4)) == 0);
-#pragma unroll
-            for (int r = 0; r < E; ++r) xch[r * T + tid] = v[r];
-            __syncthreads();
-#pragma unroll
-            for (int r = 0; r < E; ++r) {
-                const unsigned p = xch[r * T + pt];
-                v[r] = keep_min ? min(v[r], p) : max(v[r], p);
-            }
-            __syncthreads();
-        }
-#pragma unroll
-        for (int jl = 16; jl >= 1; jl >>= 1) {                  // partner in another lane: j = 16 * jl
-            if (16 * jl < k) {
-                const bool keep_min = asc == ((tid & jl) == 0);
-#pragma unroll
-                for (int r = 0; r < E; ++r) {
-                    const unsigned p = __shfl_xor_sync(kFull, v[r], jl);
-                    v[r] = keep_min ? min(v[r], p) : max(v[r], p);
-                }
-            }
-        }
-        reg_stage(std::integral_constant<int, 8>{}, asc);
-        reg_stage(std::integral_constant<int, 4>{}, asc);
-        reg_stage(std::integral_constant<int, 2>{}, asc);
-        reg_stage(std::integral_constant<int, 1>{}, asc);
-    }
+    fps_sort_keys<E, T>(v, xch, tid);
     // thread t now holds sorted positions t*16 .. t*16+15 (padding keys last: position >= n <=> padding)
 #pragma unroll
     for (int r0 = 0; r0 < E; r0 += 4) {     // four positions at a time: 16-byte stores, few live registers
