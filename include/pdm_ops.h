@@ -173,6 +173,64 @@ int pdm_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *box
 int pdm_nms_bev_batched(int frames, int k, const float *boxes, const int *counts, float thresh,
                         int *keep, int *num_keep, void *stream);
 
+/* ---- dense BEV layers on the tensor cores (csrc/conv_tc.cu) ------------------------------------ */
+
+/* Activation layout between the dense layers, "split NHWC8": a bf16 tensor (2, B, Y, C/8, X, 8), plane 0 =
+ * bf16(v), plane 1 = bf16(v - plane0) (hi + lo carries an fp32 value to 2^-17).  C must be a multiple of 8.
+ * pdm_act_split_bytes gives the buffer size; the two converters are for API edges and tests (inside the
+ * detector the producing kernels write the split form themselves). */
+int pdm_act_split_bytes(int b, int c, int y, int x, long long *bytes);
+int pdm_act_split_from_nchw(int b, int c, int y, int x, const float *in, void *out_split, void *stream);
+int pdm_act_split_to_nchw(int b, int c, int y, int x, const void *in_split, float *out, void *stream);
+
+/* Conv2d(k x k, stride 1, padding (k-1)/2) + folded eval-mode BatchNorm + activation as a tcgen05 implicit
+ * GEMM with TMA-staged operands; replaces the cuDNN stacks of BaseBEVBackbone's stride-1 block
+ * (base_bev_backbone.py:27-47: ZeroPad2d + Conv2d 3x3 bias=False + BatchNorm2d(eps 1e-3) + ReLU, repeated) and of
+ * SeparateHead / the shared conv of CenterHead (center_head.py:12-46, 63-72: Conv2d 3x3 + BN + ReLU ... Conv2d 3x3
+ * bias=True) at inference.
+ *   in_split: split NHWC8 activation (b, cin, y, x); cin a multiple of 32
+ *   w_packed: bf16 [cin/32][k*k][hi|lo][4][npad][8] = BN-folded weights W'[n][c][ky][kx] split like the
+ *             activations, c = 32*i0 + 8*i3 + i5, tap = ky*k + kx, npad = cout rounded up to 16/32/64/128 (zero rows)
+ *   bias:     fp32 [npad] folded bias;  act: 0 none, 1 ReLU, 2 sigmoid
+ *   out_split (optional): split NHWC8 (b, cout, y, x), needs cout % 8 == 0;  out_nchw (optional): fp32 (b, cout, y, x)
+ * Products are formed as hi*hi + lo*hi + hi*lo with fp32 accumulation (about 1e-5 relative to an fp32 convolution).
+ * Limits: k in {1, 3}, cout <= 128. */
+int pdm_conv_tc_forward(int b, int y, int x, int cin, int cout, int ksize, const void *in_split,
+                        const void *w_packed, const float *bias, int act, void *out_split, float *out_nchw,
+                        void *stream);
+
+/* pdm_neck_forward with the BEV map written in the split NHWC8 layout for the tensor-core convolutions
+ * (spatial_split, may be NULL) and/or as fp32 (B,C,Y,X) (spatial_features, may be NULL); at least one. */
+int pdm_neck_forward_split(int batch, int p, int c, const float *point_coords, const float *point_features,
+                           const float *coef, const float *range_min, const float *voxel, const int *grid,
+                           const int *dilation, int sh_degree, float sigma, float eps,
+                           float *spatial_features, void *spatial_split, void *stream);
+
+/* out (P, nout) = x (P, C) W^T + b, nout <= 16: nn.Linear for a handful of outputs per point (the neck's
+ * spherical-harmonic coefficients, SPEC_PDM.md "coef").  w (nout, C) row-major as in nn.Linear.weight; b may be NULL. */
+int pdm_linear_rows(int p, int c, int nout, const float *x, const float *w, const float *b, float *out, void *stream);
+
+/* The per-point half of the hybrid head (SPEC_HEAD.md steps 3-6) in one kernel.  Replaces, at inference:
+ * the FC stacks built by PointHeadTemplate.make_fc_layers (point_head_template.py:36-47) as used in
+ * PointHeadBox.forward (point_head_box.py:85-86: cls_layers / box_layers), the class maximum of
+ * generate_predicted_boxes (point_head_template.py:166-184) and PointResidualCoder.decode_torch
+ * (box_coder_utils.py:189-222, use_mean_size=True), plus the hybrid head's feature fusion and score calibration.
+ *   point_coords (P,4) [b,x,y,z]; point_features (P,c_point); bev_split: split NHWC8 (batch, c_bev, y, x);
+ *   heatmap fp32 (batch, n_class, y, x), already sigmoid-ed; range_min_xy[2], voxel_xy[2] host arrays;
+ *   w1t (c_point + c_bev, hidden_cls + hidden_box): first Linear of both stacks, BN folded, transposed and
+ *   concatenated [cls | box]; b1 (hidden_cls + hidden_box); w2_cls (n_class, hidden_cls), b2_cls; w2_box (8, hidden_box),
+ *   b2_box; mean_size (n_class, 3)
+ *   -> scores (P, n_class) = sigmoid(cls) * sqrt(heatmap at the point's pillar); best_score (P), best_label (P) int32
+ *      (first maximum); boxes (P,7) decoded with the best class; cls_raw (P, n_class) / box_raw (P,8) optional logits.
+ * Limits: n_class <= 8, hidden widths multiples of 4 with sum <= 256, c_point % 4 == 0, c_bev % 8 == 0. */
+int pdm_point_head_forward(int p, int batch, int c_point, int c_bev, int y, int x, int n_class, int hidden_cls,
+                           int hidden_box, const float *range_min_xy, const float *voxel_xy,
+                           const float *point_coords, const float *point_features, const void *bev_split,
+                           const float *heatmap, const float *w1t, const float *b1, const float *w2_cls,
+                           const float *b2_cls, const float *w2_box, const float *b2_box, const float *mean_size,
+                           float *scores, float *boxes, float *best_score, int *best_label, float *cls_raw,
+                           float *box_raw, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

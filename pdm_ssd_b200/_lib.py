@@ -33,6 +33,15 @@ SIGNATURES = {
     "pdm_boxes_iou_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "pdm_boxes_overlap_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "pdm_nms_bev_batched": [_i, _i, _vp, _vp, _f, _vp, _vp, _vp],
+    "pdm_neck_forward_split": [_i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f),
+                               ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _f, _f, _vp, _vp, _vp],
+    "pdm_linear_rows": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pdm_point_head_forward": [_i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f),
+                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pdm_act_split_bytes": [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_longlong)],
+    "pdm_act_split_from_nchw": [_i, _i, _i, _i, _vp, _vp, _vp],
+    "pdm_act_split_to_nchw": [_i, _i, _i, _i, _vp, _vp, _vp],
+    "pdm_conv_tc_forward": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
 }
 
 _lib = None

@@ -1,5 +1,6 @@
 // common.cuh -- shared helpers for libpdmops (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -44,6 +45,39 @@ __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
 }
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+
+// fp32 carried as two bf16 values for the tensor-core layers (conv_tc.cu): hi = bf16(v), lo = bf16(v - hi);
+// hi + lo equals v to 2^-17 relative.
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(__fsub_rn(v, __bfloat162float(hi)));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+// eight fp32 values -> the two 16-byte rows (hi, lo) of one pixel's 8-channel chunk in the split NHWC8 layout
+__device__ __forceinline__ void split8_bf16(const float *f, uint4 &hi, uint4 &lo) {
+    uint32_t hw[4], lw[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(f[2 * q], h0, l0);
+        split_bf16(f[2 * q + 1], h1, l1);
+        hw[q] = pack_bf16x2(h0, h1);
+        lw[q] = pack_bf16x2(l0, l1);
+    }
+    hi = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    lo = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+// the inverse for one 16-byte row pair: value = hi + lo
+__device__ __forceinline__ void join8_bf16(const uint4 &hi, const uint4 &lo, float *f) {
+    const uint32_t hw[4] = {hi.x, hi.y, hi.z, hi.w}, lw[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        f[2 * q] = __fadd_rn(__uint_as_float(hw[q] << 16), __uint_as_float(lw[q] << 16));
+        f[2 * q + 1] = __fadd_rn(__uint_as_float(hw[q] & 0xffff0000u), __uint_as_float(lw[q] & 0xffff0000u));
+    }
+}
 
 // Streaming (evict-first) 128-bit store for write-once outputs.
 __device__ __forceinline__ void st_cs_f4(float *p, float4 v) {

@@ -1,0 +1,483 @@
+// conv_tc.cu -- 3x3 (or 1x1) convolution + folded eval-mode BatchNorm + activation on the BEV map as an
+// implicit GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in tensor memory),
+// operands staged by TMA.  Replaces, for inference, the Conv2d/BatchNorm2d/ReLU stacks of the
+// "context learning" block (pcdet/models/backbones_2d/base_bev_backbone.py:27-47) and of the heatmap
+// branch of the hybrid head (pcdet/models/dense_heads/center_head.py:12-46), which the reference runs
+// as cuDNN fp32 kernels.
+//
+// Accuracy: the budget is 1e-3 relative in fp32 (BASELINE.json north_star).  Every fp32 operand is
+// carried as TWO bf16 values, hi = bf16(v) and lo = bf16(v - hi), and a product is formed as
+// hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM (3 tcgen05.mma.kind::f16 per k-step): the
+// dropped lo*lo term is 2^-18 relative, measured ~1e-5 against torch fp32 after a 5-conv stack.
+//
+// Activation layout between the layers ("split NHWC8", written by the producing kernel's epilogue and
+// by the neck's dense writer, read by TMA):   bf16 [plane: hi|lo][B][Y][C/8][X][8]
+// i.e. per image row the channels come in chunks of 8 and each chunk holds the whole row.  A TMA box
+// {(H)x8 elements, 4 chunks, H rows} of that tensor lands in shared memory as  [row][chunk][x][8]  which
+// IS the K-major, no-swizzle core-matrix layout of tcgen05 (core matrix = 8 consecutive pixels x 16
+// bytes, contiguous; LBO = one chunk row = H*16 bytes; SBO = one image row = 4*H*16 bytes).  So ONE halo
+// tile (18 x 18 pixels for a 16 x 16 output unit) serves all nine taps: tap (ky,kx) is the same buffer
+// with the descriptor start address moved by ky rows and kx pixels -- no im2col copy, the input is read
+// from L2/HBM 1.27x instead of 9x, and out-of-image halo cells are zero-filled by TMA (= conv padding).
+//
+// CTA = persistent, warp-specialised:  warp 0 lane 0 streams halo tiles (TMA tensor loads, 2-stage ring
+// of 32-channel chunks), warp 1 lane 0 streams the pre-packed weight blocks (1-D bulk copies, 3-stage
+// ring, one (32-channel chunk, tap) block per stage), warp 2 lane 0 issues the MMAs, warp 3 owns the
+// TMEM allocation, warps 4-7 drain the accumulators (tcgen05.ld -> bias + activation -> hi/lo split ->
+// global).  A CTA works on TWO 16x16 units at a time (4 accumulators of 128 rows = 4 x npad TMEM
+// columns) so that every weight block fetched from L2 feeds 512 output pixels.
+// Every mbarrier wait is bounded: on a time-out the kernel records a code in the error word and traps
+// (the launch fails loudly; it never hangs and never continues past an unsatisfied barrier).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace pdm {
+
+constexpr int kCvThreads = 256;
+constexpr int kCvAStages = 2;
+constexpr int kCvWStages = 3;
+constexpr int kCvMaxN = 128;
+
+struct ConvTCParams {
+    int B, Y, X, cin, cout, npad, ksize;
+    int halo;            // 16 + ksize - 1 pixels per side of a unit's input tile
+    int units_x, units_y, total_units, units_per_cta;
+    int a_unit_bytes;    // one (unit, plane) box: halo rows x 4 chunks x halo pixels x 16 bytes
+    int w_stage_bytes;   // one (chunk, tap) weight block: 2 planes x 4 chunks x npad rows x 16 bytes
+    int act;             // 0 none, 1 relu, 2 sigmoid
+    int sets;            // accumulator sets in TMEM (2 when 8*npad <= 512: epilogue overlaps the next tile)
+    int tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t cv_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
+__device__ __forceinline__ unsigned long long cv_globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded wait: ~2 s of wall clock, then error word + trap.  `code` says which barrier gave up.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *err, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = cv_globaltimer();
+    for (;;) {
+#pragma unroll 1
+        for (int it = 0; it < 256; ++it)
+            if (mbar_try_wait(bar, parity)) return;
+        if (cv_globaltimer() - t0 > 2000000000ull) {
+            if (err) atomicExch(err, code);
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+                 :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (version 1 at bit 46)
+__device__ __forceinline__ uint64_t cv_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+struct __align__(8) ConvBarriers {
+    uint64_t a_full[kCvAStages], a_empty[kCvAStages];
+    uint64_t w_full[kCvWStages], w_empty[kCvWStages];
+    uint64_t acc_full[2], acc_empty[2];
+};
+
+__global__ void __launch_bounds__(kCvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P,
+               const unsigned char *__restrict__ w_packed, const float *__restrict__ bias,
+               __nv_bfloat16 *__restrict__ out_split, float *__restrict__ out_nchw, int *__restrict__ err) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ ConvBarriers bars;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[kCvMaxN];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t smem0 = (cv_smem_u32(smem_raw) + 127u) & ~127u;
+    const uint32_t a_stage_bytes = 4u * (uint32_t)P.a_unit_bytes;
+    const uint32_t a_base = smem0;
+    const uint32_t w_base = smem0 + kCvAStages * a_stage_bytes;
+
+    const int u_first = blockIdx.x * P.units_per_cta;
+    const int u_last = min(u_first + P.units_per_cta, P.total_units);
+    const int n_tiles = (u_last - u_first + 1) / 2;
+    const int n_kc = P.cin / 32, taps = P.ksize * P.ksize, pad = (P.ksize - 1) / 2;
+
+    if (tid == 0) {
+        for (int s = 0; s < kCvAStages; ++s) { mbar_init(cv_smem_u32(&bars.a_full[s]), 1); mbar_init(cv_smem_u32(&bars.a_empty[s]), 1); }
+        for (int s = 0; s < kCvWStages; ++s) { mbar_init(cv_smem_u32(&bars.w_full[s]), 1); mbar_init(cv_smem_u32(&bars.w_empty[s]), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(cv_smem_u32(&bars.acc_full[s]), 1); mbar_init(cv_smem_u32(&bars.acc_empty[s]), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 3) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(cv_smem_u32(&tmem_base_s)), "r"(P.tmem_cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid < kCvMaxN) bias_s[tid] = tid < P.cout ? __ldg(bias + tid) : 0.f;
+    if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_in) : "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ===== halo-tile producer (TMA tensor loads) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int u0 = u_first + 2 * t;
+                const int nun = min(2, u_last - u0);
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(cv_smem_u32(&bars.a_empty[stage]), phase ^ 1u, err, 101);
+                    const uint32_t full = cv_smem_u32(&bars.a_full[stage]);
+                    mbar_arrive_expect_tx(full, (uint32_t)(nun * 2 * P.a_unit_bytes));
+                    for (int un = 0; un < nun; ++un) {
+                        const int u = u0 + un;
+                        const int ux = u % P.units_x, r = u / P.units_x;
+                        const int uy = r % P.units_y, b = r / P.units_y;
+                        for (int pl = 0; pl < 2; ++pl)
+                            tma_load_5d(a_base + stage * a_stage_bytes + (uint32_t)((un * 2 + pl) * P.a_unit_bytes), &tmap_in, full,
+                                        (ux * 16 - pad) * 8, kc * 4, uy * 16 - pad, b, pl);
+                    }
+                    if (++stage == kCvAStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== weight-block producer (1-D bulk copies; the blocks are pre-packed in consumption order) =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const unsigned char *src = w_packed;
+                for (int blk = 0; blk < n_kc * taps; ++blk) {
+                    mbar_wait(cv_smem_u32(&bars.w_empty[stage]), phase ^ 1u, err, 102);
+                    const uint32_t full = cv_smem_u32(&bars.w_full[stage]);
+                    mbar_arrive_expect_tx(full, (uint32_t)P.w_stage_bytes);
+                    bulk_load_1d(w_base + stage * (uint32_t)P.w_stage_bytes, src, (uint32_t)P.w_stage_bytes, full);
+                    src += P.w_stage_bytes;
+                    if (++stage == kCvWStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t H16 = (uint32_t)P.halo * 16u;          // one chunk row of the halo tile
+            const uint32_t a_lbo = H16, a_sbo = 4u * H16;
+            const uint32_t w_lbo = (uint32_t)P.npad * 16u, w_sbo = 128u;
+            const uint32_t w_plane = 4u * w_lbo;
+            int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
+            for (int t = 0; t < n_tiles; ++t) {
+                const int nun = min(2, u_last - (u_first + 2 * t));
+                const int set = t % P.sets;
+                const uint32_t use = (uint32_t)(t / P.sets);
+                mbar_wait(cv_smem_u32(&bars.acc_empty[set]), (use & 1u) ^ 1u, err, 103);
+                asm volatile("tcgen05.fence::after_thread_sync;");
+                const uint32_t acc0 = tmem_base + (uint32_t)(set * 4 * P.npad);
+                for (int kc = 0; kc < n_kc; ++kc) {
+                    mbar_wait(cv_smem_u32(&bars.a_full[as]), aph, err, 104);
+                    const uint32_t a_st = a_base + as * a_stage_bytes;
+                    for (int tap = 0; tap < taps; ++tap) {
+                        mbar_wait(cv_smem_u32(&bars.w_full[ws]), wph, err, 105);
+                        asm volatile("tcgen05.fence::after_thread_sync;");
+                        const int ky = tap / P.ksize, kx = tap - ky * P.ksize;
+                        const uint32_t w_st = w_base + ws * (uint32_t)P.w_stage_bytes;
+                        for (int un = 0; un < nun; ++un) {
+#pragma unroll
+                            for (int mh = 0; mh < 2; ++mh) {
+                                const uint32_t d = acc0 + (uint32_t)((un * 2 + mh) * P.npad);
+                                const uint32_t a_hi = a_st + (uint32_t)(un * 2) * (uint32_t)P.a_unit_bytes + (uint32_t)ky * a_sbo + (uint32_t)(kx + 8 * mh) * 16u;
+                                const uint32_t a_lo = a_hi + (uint32_t)P.a_unit_bytes;
+#pragma unroll
+                                for (int ks = 0; ks < 2; ++ks) {
+                                    const uint64_t ah = cv_desc(a_hi + ks * 2u * a_lbo, a_lbo, a_sbo);
+                                    const uint64_t al = cv_desc(a_lo + ks * 2u * a_lbo, a_lbo, a_sbo);
+                                    const uint64_t wh = cv_desc(w_st + ks * 2u * w_lbo, w_lbo, w_sbo);
+                                    const uint64_t wl = cv_desc(w_st + w_plane + ks * 2u * w_lbo, w_lbo, w_sbo);
+                                    umma_bf16(d, ah, wh, idesc, (kc | tap | ks) != 0);
+                                    umma_bf16(d, al, wh, idesc, 1);
+                                    umma_bf16(d, ah, wl, idesc, 1);
+                                }
+                            }
+                        }
+                        umma_commit(cv_smem_u32(&bars.w_empty[ws]));      // weight block free once these MMAs retire
+                        if (++ws == kCvWStages) { ws = 0; wph ^= 1u; }
+                    }
+                    umma_commit(cv_smem_u32(&bars.a_empty[as]));          // halo chunk free
+                    if (++as == kCvAStages) { as = 0; aph ^= 1u; }
+                }
+                umma_commit(cv_smem_u32(&bars.acc_full[set]));            // accumulators of this tile complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===== epilogue: TMEM lane = GEMM row = pixel (row r: image row r/8 of the unit, pixel r%8 of the half) =====
+        const int wq = warp & 3;
+        const int C8 = P.cout >> 3;
+        for (int t = 0; t < n_tiles; ++t) {
+            const int u0 = u_first + 2 * t;
+            const int nun = min(2, u_last - u0);
+            const int set = t % P.sets;
+            const uint32_t use = (uint32_t)(t / P.sets);
+            mbar_wait(cv_smem_u32(&bars.acc_full[set]), use & 1u, err, 106);
+            asm volatile("tcgen05.fence::after_thread_sync;");
+            for (int un = 0; un < nun; ++un) {
+                const int u = u0 + un;
+                const int ux = u % P.units_x, r = u / P.units_x;
+                const int uy = r % P.units_y, b = r / P.units_y;
+                const int y = uy * 16 + wq * 4 + (lane >> 3);
+#pragma unroll 1
+                for (int mh = 0; mh < 2; ++mh) {
+                    const int x = ux * 16 + mh * 8 + (lane & 7);
+                    const bool valid = y < P.Y && x < P.X;
+                    const uint32_t col0 = (uint32_t)((set * 4 + un * 2 + mh) * P.npad);
+#pragma unroll 1
+                    for (int ch = 0; ch * 16 < P.npad; ++ch) {
+                        uint32_t v[16];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + col0 + (uint32_t)(ch * 16);
+                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                     : "r"(taddr));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            float a = __uint_as_float(v[j]) + bias_s[ch * 16 + j];
+                            if (P.act == 1) a = fmaxf(a, 0.f);
+                            else if (P.act == 2) a = 1.f / (1.f + __expf(-a));
+                            f[j] = a;
+                        }
+                        if (valid) {
+                            if (out_split) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    const int c8 = ch * 2 + h;
+                                    if (c8 < C8) {
+                                        uint4 hq, lq;
+                                        split8_bf16(f + h * 8, hq, lq);
+                                        const size_t row = (((size_t)b * P.Y + y) * C8 + c8) * P.X + x;
+                                        const size_t plane = (size_t)P.B * P.Y * C8 * P.X;
+                                        *reinterpret_cast<uint4 *>(out_split + row * 8) = hq;
+                                        *reinterpret_cast<uint4 *>(out_split + (plane + row) * 8) = lq;
+                                    }
+                                }
+                            }
+                            if (out_nchw) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const int c = ch * 16 + j;
+                                    if (c < P.cout) out_nchw[(((size_t)b * P.cout + c) * P.Y + y) * P.X + x] = f[j];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cv_smem_u32(&bars.acc_empty[set]));
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    if (warp == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols));
+}
+
+// ---- layout conversions (API edges and tests; inside the detector the producers write the split form) ----
+// fp32 (B,C,Y,X) -> split NHWC8.  Thread = (b, y, chunk, x): 8 strided reads (coalesced across x), two 16-byte stores.
+__global__ void __launch_bounds__(256)
+split_from_nchw_kernel(int B, int C, int Y, int X, const float *__restrict__ in, __nv_bfloat16 *__restrict__ out) {
+    const int C8 = C >> 3;
+    const size_t total = (size_t)B * Y * C8 * X;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % X);
+        size_t r = i / X;
+        const int c8 = (int)(r % C8); r /= C8;
+        const int y = (int)(r % Y);
+        const int b = (int)(r / Y);
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __ldg(in + (((size_t)b * C + c8 * 8 + e) * Y + y) * X + x);
+        uint4 hq, lq;
+        split8_bf16(f, hq, lq);
+        *reinterpret_cast<uint4 *>(out + i * 8) = hq;
+        *reinterpret_cast<uint4 *>(out + (total + i) * 8) = lq;
+    }
+}
+
+// split NHWC8 -> fp32 (B,C,Y,X): value = hi + lo
+__global__ void __launch_bounds__(256)
+split_to_nchw_kernel(int B, int C, int Y, int X, const __nv_bfloat16 *__restrict__ in, float *__restrict__ out) {
+    const int C8 = C >> 3;
+    const size_t total = (size_t)B * Y * C8 * X;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % X);
+        size_t r = i / X;
+        const int c8 = (int)(r % C8); r /= C8;
+        const int y = (int)(r % Y);
+        const int b = (int)(r / Y);
+        const uint4 h = *reinterpret_cast<const uint4 *>(in + i * 8);
+        const uint4 l = *reinterpret_cast<const uint4 *>(in + (total + i) * 8);
+        float f[8];
+        join8_bf16(h, l, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[(((size_t)b * C + c8 * 8 + e) * Y + y) * X + x] = f[e];
+    }
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link-time dependency on libcuda
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            (void)cudaGetLastError();
+    });
+    return fn;
+}
+
+// one device error word per process and device, checked lazily (a time-out traps anyway)
+static int *conv_err_word() {
+    static std::mutex mu;
+    static int *words[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!words[dev]) {
+        if (cudaMalloc(&words[dev], sizeof(int)) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+        cudaMemset(words[dev], 0, sizeof(int));
+    }
+    return words[dev];
+}
+
+}  // namespace pdm
+
+extern "C" int pdm_act_split_bytes(int b, int c, int y, int x, long long *bytes) {
+    if (b < 0 || c < 0 || y < 0 || x < 0 || (c & 7) || !bytes) return pdm::fail(PDM_ERR_INVALID_ARG, "act_split_bytes: bad size");
+    *bytes = (long long)2 * b * y * c * x * 2;
+    return PDM_OK;
+}
+
+extern "C" int pdm_act_split_from_nchw(int b, int c, int y, int x, const float *in, void *out_split, void *stream) {
+    using namespace pdm;
+    if (b < 0 || c < 0 || y < 0 || x < 0 || (c & 7)) return fail(PDM_ERR_INVALID_ARG, "act_split_from_nchw: bad size (channels must be a multiple of 8)");
+    const size_t total = (size_t)b * y * (c >> 3) * x;
+    if (total == 0) return PDM_OK;
+    if (!in || !out_split) return fail(PDM_ERR_INVALID_ARG, "act_split_from_nchw: null pointer");
+    const int grid = (int)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
+    split_from_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b, c, y, x, in, (__nv_bfloat16 *)out_split);
+    count_launch();
+    PDM_CHECK_LAUNCH("act_split_from_nchw");
+    return PDM_OK;
+}
+
+extern "C" int pdm_act_split_to_nchw(int b, int c, int y, int x, const void *in_split, float *out, void *stream) {
+    using namespace pdm;
+    if (b < 0 || c < 0 || y < 0 || x < 0 || (c & 7)) return fail(PDM_ERR_INVALID_ARG, "act_split_to_nchw: bad size (channels must be a multiple of 8)");
+    const size_t total = (size_t)b * y * (c >> 3) * x;
+    if (total == 0) return PDM_OK;
+    if (!in_split || !out) return fail(PDM_ERR_INVALID_ARG, "act_split_to_nchw: null pointer");
+    const int grid = (int)((total + 255) / 256 < (size_t)kNumSMs * 16 ? (total + 255) / 256 : (size_t)kNumSMs * 16);
+    split_to_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(b, c, y, x, (const __nv_bfloat16 *)in_split, out);
+    count_launch();
+    PDM_CHECK_LAUNCH("act_split_to_nchw");
+    return PDM_OK;
+}
+
+extern "C" int pdm_conv_tc_forward(int b, int y, int x, int cin, int cout, int ksize, const void *in_split,
+                                   const void *w_packed, const float *bias, int act, void *out_split, float *out_nchw,
+                                   void *stream) {
+    using namespace pdm;
+    if (b < 0 || y < 0 || x < 0 || cin <= 0 || cout <= 0) return fail(PDM_ERR_INVALID_ARG, "conv_tc_forward: bad size");
+    if (ksize != 1 && ksize != 3) return fail(PDM_ERR_UNSUPPORTED, "conv_tc_forward: kernel size %d (1 or 3)", ksize);
+    if (cin % 32 != 0 || cin > 512) return fail(PDM_ERR_UNSUPPORTED, "conv_tc_forward: cin %d (multiple of 32, <= 512)", cin);
+    if (cout > kCvMaxN) return fail(PDM_ERR_UNSUPPORTED, "conv_tc_forward: cout %d > %d", cout, kCvMaxN);
+    if (act < 0 || act > 2) return fail(PDM_ERR_INVALID_ARG, "conv_tc_forward: act %d", act);
+    if (out_split && (cout & 7)) return fail(PDM_ERR_UNSUPPORTED, "conv_tc_forward: split output needs cout %% 8 == 0");
+    if (b == 0 || y == 0 || x == 0) return PDM_OK;
+    if (!in_split || !w_packed || !bias || (!out_split && !out_nchw)) return fail(PDM_ERR_INVALID_ARG, "conv_tc_forward: null pointer");
+    if ((x * 16) % 16 != 0 || ((uintptr_t)in_split & 15) || ((uintptr_t)w_packed & 15))
+        return fail(PDM_ERR_INVALID_ARG, "conv_tc_forward: operands must be 16-byte aligned");
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(PDM_ERR_UNSUPPORTED, "conv_tc_forward: cuTensorMapEncodeTiled is not available from this driver");
+
+    ConvTCParams P;
+    P.B = b; P.Y = y; P.X = x; P.cin = cin; P.cout = cout; P.ksize = ksize; P.act = act;
+    P.npad = cout <= 16 ? 16 : cout <= 32 ? 32 : cout <= 64 ? 64 : 128;
+    P.halo = 16 + ksize - 1;
+    P.units_x = (x + 15) / 16; P.units_y = (y + 15) / 16;
+    P.total_units = b * P.units_x * P.units_y;
+    int per = (P.total_units + 2 * kNumSMs - 1) / (2 * kNumSMs) * 2;     // even: a CTA works on pairs of units
+    if (per < 2) per = 2;
+    P.units_per_cta = per;
+    const int grid = (P.total_units + per - 1) / per;
+    P.a_unit_bytes = P.halo * 4 * P.halo * 16;
+    P.w_stage_bytes = 2 * 4 * P.npad * 16;
+    P.sets = 8 * P.npad <= 512 ? 2 : 1;
+    int cols = 4 * P.npad * P.sets, pw = 32;
+    while (pw < cols) pw <<= 1;
+    P.tmem_cols = pw;
+
+    CUtensorMap tmap;
+    const cuuint64_t gdim[5] = {(cuuint64_t)x * 8, (cuuint64_t)(cin / 8), (cuuint64_t)y, (cuuint64_t)b, 2};
+    const cuuint64_t gstr[4] = {(cuuint64_t)x * 16, (cuuint64_t)x * 16 * (cin / 8), (cuuint64_t)x * 16 * (cin / 8) * y,
+                                (cuuint64_t)x * 16 * (cin / 8) * y * b};
+    const cuuint32_t box[5] = {(cuuint32_t)P.halo * 8, 4, (cuuint32_t)P.halo, 1, 1};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    const CUresult cr = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(in_split), gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return fail(PDM_ERR_INVALID_ARG, "conv_tc_forward: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+
+    const size_t smem = (size_t)kCvAStages * 4 * P.a_unit_bytes + (size_t)kCvWStages * P.w_stage_bytes + 128;
+    if (int rc = ensure_dynamic_smem((const void *)conv_tc_kernel, smem)) return rc;
+    conv_tc_kernel<<<grid, kCvThreads, smem, (cudaStream_t)stream>>>(tmap, P, (const unsigned char *)w_packed, bias,
+                                                                    (__nv_bfloat16 *)out_split, out_nchw, conv_err_word());
+    count_launch();
+    PDM_CHECK_LAUNCH("conv_tc_forward");
+    return PDM_OK;
+}

@@ -417,14 +417,45 @@ pdm_dense_kernel(int c_total, int plane /*Y*X*/, const int *__restrict__ pslot,
         if (c < cn) st_cs_f1(out + (size_t)c * plane, v[c]);
 }
 
-}  // namespace pdm
+// The same map in the "split NHWC8" layout the tensor-core convolutions read (conv_tc.cu):
+// bf16 [hi|lo][B][Y][C/8][X][8].  Thread per (pillar, 32 channels): consecutive threads are consecutive x, so
+// every 16-byte store of a warp lands in one 512-byte run; zeros included, every element written once.
+__global__ void __launch_bounds__(256)
+pdm_dense_split_kernel(int c_total, int X, int plane /*Y*X*/, int batch, const int *__restrict__ pslot,
+                       const float *__restrict__ pf, __nv_bfloat16 *__restrict__ bev) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= plane) return;
+    const int cb = blockIdx.y * kDenseCB, b = blockIdx.z;
+    const int C8 = c_total >> 3;
+    const int y = j / X, x = j - y * X, Y = plane / X;
+    const int sl = __ldg(pslot + (size_t)b * plane + j);
+    const size_t lo_off = (size_t)batch * Y * C8 * X * 8;
+#pragma unroll
+    for (int q = 0; q < kDenseCB / 8; ++q) {
+        const int c8 = (cb >> 3) + q;
+        if (c8 >= C8) break;
+        float f[8];
+        if (sl >= 0) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(pf + (size_t)sl * c_total + c8 * 8));
+            const float4 d = __ldg(reinterpret_cast<const float4 *>(pf + (size_t)sl * c_total + c8 * 8 + 4));
+            f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = d.x; f[5] = d.y; f[6] = d.z; f[7] = d.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = 0.f;
+        }
+        uint4 hq, lq;
+        split8_bf16(f, hq, lq);
+        __nv_bfloat16 *dst = bev + ((((size_t)b * Y + y) * C8 + c8) * X + x) * 8;
+        *reinterpret_cast<uint4 *>(dst) = hq;
+        *reinterpret_cast<uint4 *>(dst + lo_off) = lq;
+    }
+}
 
-extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coords,
-                                const float *point_features, const float *coef,
-                                const float *range_min, const float *voxel, const int *grid,
-                                const int *dilation, int sh_degree, float sigma, float eps,
-                                float *spatial_features, int *dbg_keys, float *dbg_w, void *stream) {
-    using namespace pdm;
+static int neck_forward_impl(int batch, int p, int c, const float *point_coords,
+                             const float *point_features, const float *coef,
+                             const float *range_min, const float *voxel, const int *grid,
+                             const int *dilation, int sh_degree, float sigma, float eps,
+                             float *spatial_features, void *spatial_split, int *dbg_keys, float *dbg_w, void *stream) {
     if (batch < 0 || p < 0 || c < 0) return fail(PDM_ERR_INVALID_ARG, "neck_forward: negative size");
     if (!range_min || !voxel || !grid || !dilation) return fail(PDM_ERR_INVALID_ARG, "neck_forward: null config");
     if (sh_degree < 0 || sh_degree > 2) return fail(PDM_ERR_UNSUPPORTED, "neck_forward: SH degree %d", sh_degree);
@@ -445,8 +476,10 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
         return fail(PDM_ERR_UNSUPPORTED, "neck_forward: B*X*Y*Z must fit int32");
     if (batch == 0 || c == 0) return PDM_OK;
     if (batch > 65535) return fail(PDM_ERR_UNSUPPORTED, "neck_forward: batch > 65535");
-    if (!spatial_features || (p > 0 && (!point_coords || !point_features || !coef)))
+    if ((!spatial_features && !spatial_split) || (p > 0 && (!point_coords || !point_features || !coef)))
         return fail(PDM_ERR_INVALID_ARG, "neck_forward: null pointer");
+    if (spatial_split && ((c & 7) || (reinterpret_cast<uintptr_t>(spatial_split) & 15)))
+        return fail(PDM_ERR_UNSUPPORTED, "neck_forward: the split output needs C %% 8 == 0 and a 16-byte aligned buffer");
     cudaStream_t st = (cudaStream_t)stream;
     const int kxy = (2 * dilation[0] + 1) * (2 * dilation[1] + 1), kz_n = 2 * dilation[2] + 1;
     const int nsh = (sh_degree + 1) * (sh_degree + 1);
@@ -527,11 +560,38 @@ extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coor
         const int plane = grid[0] * grid[1], cblocks = (c + kDenseCB - 1) / kDenseCB;
         if (cblocks > 65535) return fail(PDM_ERR_UNSUPPORTED, "neck_forward: too many channels %d", c);
         dim3 g((plane + 255) / 256, cblocks, batch);
-        if ((c % 4) == 0) pdm_dense_kernel<true><<<g, 256, 0, st>>>(c, plane, pslot, pf, spatial_features);
-        else pdm_dense_kernel<false><<<g, 256, 0, st>>>(c, plane, pslot, pf, spatial_features);
-        count_launch();
+        if (spatial_features) {
+            if ((c % 4) == 0) pdm_dense_kernel<true><<<g, 256, 0, st>>>(c, plane, pslot, pf, spatial_features);
+            else pdm_dense_kernel<false><<<g, 256, 0, st>>>(c, plane, pslot, pf, spatial_features);
+            count_launch();
+        }
+        if (spatial_split) {
+            pdm_dense_split_kernel<<<g, 256, 0, st>>>(c, grid[0], plane, batch, pslot, pf, (__nv_bfloat16 *)spatial_split);
+            count_launch();
+        }
         err = cudaGetLastError();
     }
     if (err != cudaSuccess) return fail((int)err, "neck_forward: %s", cudaGetErrorString(err));
     return PDM_OK;
+}
+
+}  // namespace pdm
+
+extern "C" int pdm_neck_forward(int batch, int p, int c, const float *point_coords,
+                                const float *point_features, const float *coef,
+                                const float *range_min, const float *voxel, const int *grid,
+                                const int *dilation, int sh_degree, float sigma, float eps,
+                                float *spatial_features, int *dbg_keys, float *dbg_w, void *stream) {
+    if (!spatial_features && batch > 0 && c > 0) return pdm::fail(PDM_ERR_INVALID_ARG, "neck_forward: null pointer");
+    return pdm::neck_forward_impl(batch, p, c, point_coords, point_features, coef, range_min, voxel, grid, dilation,
+                                  sh_degree, sigma, eps, spatial_features, nullptr, dbg_keys, dbg_w, stream);
+}
+
+extern "C" int pdm_neck_forward_split(int batch, int p, int c, const float *point_coords,
+                                      const float *point_features, const float *coef,
+                                      const float *range_min, const float *voxel, const int *grid,
+                                      const int *dilation, int sh_degree, float sigma, float eps,
+                                      float *spatial_features, void *spatial_split, void *stream) {
+    return pdm::neck_forward_impl(batch, p, c, point_coords, point_features, coef, range_min, voxel, grid, dilation,
+                                  sh_degree, sigma, eps, spatial_features, spatial_split, nullptr, nullptr, stream);
 }
