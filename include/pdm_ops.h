@@ -169,9 +169,18 @@ int pdm_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *box
  *   in torch first, iou3d_nms_utils.py:128-133); counts (frames) = valid boxes per frame, or NULL
  *   when every frame has k; -> keep (frames,k) int32: positions of the kept boxes in ascending
  *   order (= the reference's keep[:num_out]), padded with -1; num_keep (frames).
- * Limit: k <= 4096. */
+ * Limit: k <= 16384 (the reference takes any N; stock configs use NMS_PRE_MAXSIZE <= 9000). */
 int pdm_nms_bev_batched(int frames, int k, const float *boxes, const int *counts, float thresh,
                         int *keep, int *num_keep, void *stream);
+
+/* nms_normal_gpu (iou3d_nms_api.cpp:17, iou3d_nms.cpp:186-233, iou3d_nms_kernel.cu:341-398): the same greedy
+ * suppression on the axis-aligned BEV IoU (heading ignored); arguments as pdm_nms_bev_batched. */
+int pdm_nms_normal_batched(int frames, int k, const float *boxes, const int *counts, float thresh,
+                           int *keep, int *num_keep, void *stream);
+
+/* paired_boxes_overlap_bev_gpu / boxes_aligned_overlap_bev_gpu (iou3d_nms_api.cpp:12,14, iou3d_nms.cpp:42-66,92-111,
+ * iou3d_nms_kernel.cu:251-277): overlap area of box i of boxes_a with box i of boxes_b, (N,7) x (N,7) -> (N). */
+int pdm_boxes_overlap_bev_paired(int n, const float *boxes_a, const float *boxes_b, float *ans_overlap, void *stream);
 
 /* ---- dense BEV layers on the tensor cores (csrc/conv_tc.cu) ------------------------------------ */
 

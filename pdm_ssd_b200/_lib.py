@@ -33,6 +33,8 @@ SIGNATURES = {
     "pdm_boxes_iou_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "pdm_boxes_overlap_bev": [_i, _vp, _i, _vp, _vp, _vp],
     "pdm_nms_bev_batched": [_i, _i, _vp, _vp, _f, _vp, _vp, _vp],
+    "pdm_nms_normal_batched": [_i, _i, _vp, _vp, _f, _vp, _vp, _vp],
+    "pdm_boxes_overlap_bev_paired": [_i, _vp, _vp, _vp, _vp],
     "pdm_neck_forward_split": [_i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f),
                                ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _f, _f, _vp, _vp, _vp],
     "pdm_linear_rows": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],

@@ -39,18 +39,21 @@
 namespace pdm {
 
 constexpr int kCvThreads = 256;
-constexpr int kCvAStages = 2;
-constexpr int kCvWStages = 3;
+constexpr int kCvMaxAStages = 4;
+constexpr int kCvMaxWStages = 36;     // resident mode keeps every (chunk, tap) block: up to 4 chunks x 9 taps
 constexpr int kCvMaxN = 128;
+constexpr int kCvSmemBudget = 227 * 1024 - 1536;   // dynamic part: 227 KB per CTA minus static data and alignment slack
 
 struct ConvTCParams {
     int B, Y, X, cin, cout, npad, ksize;
     int halo;            // 16 + ksize - 1 pixels per side of a unit's input tile
     int units_x, units_y, total_units, units_per_cta;
+    int nu;              // units per tile: 2 (4 accumulators) when two sets of them fit in TMEM, else 1
     int a_unit_bytes;    // one (unit, plane) box: halo rows x 4 chunks x halo pixels x 16 bytes
     int w_stage_bytes;   // one (chunk, tap) weight block: 2 planes x 4 chunks x npad rows x 16 bytes
+    int a_stages, w_stages;
+    int w_resident;      // every weight block has its own slot: loaded once per CTA, never released
     int act;             // 0 none, 1 relu, 2 sigmoid
-    int sets;            // accumulator sets in TMEM (2 when 8*npad <= 512: epilogue overlaps the next tile)
     int tmem_cols;
 };
 
@@ -100,10 +103,11 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (version 1 at bit 46)
-__device__ __forceinline__ uint64_t cv_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) | ((uint64_t)1 << 46);
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor (version 1 at bit 46): the high word (SBO, version) is
+// fixed per operand, the low word carries the start address and LBO
+__device__ __forceinline__ uint32_t cv_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
+__device__ __forceinline__ uint64_t cv_desc(uint32_t saddr, uint32_t lbo_field, uint32_t hi) {
+    return (uint64_t)(((saddr >> 4) & 0x3fffu) | lbo_field) | ((uint64_t)hi << 32);
 }
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -114,10 +118,24 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 struct __align__(8) ConvBarriers {
-    uint64_t a_full[kCvAStages], a_empty[kCvAStages];
-    uint64_t w_full[kCvWStages], w_empty[kCvWStages];
+    uint64_t a_full[kCvMaxAStages], a_empty[kCvMaxAStages];
+    uint64_t w_full[kCvMaxWStages], w_empty[kCvMaxWStages];
     uint64_t acc_full[2], acc_empty[2];
 };
+
+// 16 accumulator values of one pixel -> bias + activation, then the two 16-byte hi/lo rows per 8-channel chunk
+__device__ __forceinline__ float cv_act(float a, int act) {
+    if (act == 1) return fmaxf(a, 0.f);
+    if (act == 2) return 1.f / (1.f + __expf(-a));
+    return a;
+}
+__device__ __forceinline__ void cv_split2(float a, float b, uint32_t &hi, uint32_t &lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);                 // one cvt for the pair
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    const float ra = a - __uint_as_float(hi << 16), rb = b - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
+}
 
 __global__ void __launch_bounds__(kCvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P,
@@ -129,18 +147,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
     __shared__ float bias_s[kCvMaxN];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t smem0 = (cv_smem_u32(smem_raw) + 127u) & ~127u;
-    const uint32_t a_stage_bytes = 4u * (uint32_t)P.a_unit_bytes;
+    const int NU = P.nu;
+    const uint32_t a_stage_bytes = (uint32_t)(2 * NU) * (uint32_t)P.a_unit_bytes;
     const uint32_t a_base = smem0;
-    const uint32_t w_base = smem0 + kCvAStages * a_stage_bytes;
+    const uint32_t w_base = smem0 + (uint32_t)P.a_stages * a_stage_bytes;
 
     const int u_first = blockIdx.x * P.units_per_cta;
     const int u_last = min(u_first + P.units_per_cta, P.total_units);
-    const int n_tiles = (u_last - u_first + 1) / 2;
+    const int n_tiles = (u_last - u_first + NU - 1) / NU;
     const int n_kc = P.cin / 32, taps = P.ksize * P.ksize, pad = (P.ksize - 1) / 2;
 
     if (tid == 0) {
-        for (int s = 0; s < kCvAStages; ++s) { mbar_init(cv_smem_u32(&bars.a_full[s]), 1); mbar_init(cv_smem_u32(&bars.a_empty[s]), 1); }
-        for (int s = 0; s < kCvWStages; ++s) { mbar_init(cv_smem_u32(&bars.w_full[s]), 1); mbar_init(cv_smem_u32(&bars.w_empty[s]), 1); }
+        for (int s = 0; s < P.a_stages; ++s) { mbar_init(cv_smem_u32(&bars.a_full[s]), 1); mbar_init(cv_smem_u32(&bars.a_empty[s]), 1); }
+        for (int s = 0; s < P.w_stages; ++s) { mbar_init(cv_smem_u32(&bars.w_full[s]), 1); mbar_init(cv_smem_u32(&bars.w_empty[s]), 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(cv_smem_u32(&bars.acc_full[s]), 1); mbar_init(cv_smem_u32(&bars.acc_empty[s]), 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -160,8 +179,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int u0 = u_first + 2 * t;
-                const int nun = min(2, u_last - u0);
+                const int u0 = u_first + NU * t;
+                const int nun = min(NU, u_last - u0);
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(cv_smem_u32(&bars.a_empty[stage]), phase ^ 1u, err, 101);
                     const uint32_t full = cv_smem_u32(&bars.a_full[stage]);
@@ -174,7 +193,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                             tma_load_5d(a_base + stage * a_stage_bytes + (uint32_t)((un * 2 + pl) * P.a_unit_bytes), &tmap_in, full,
                                         (ux * 16 - pad) * 8, kc * 4, uy * 16 - pad, b, pl);
                     }
-                    if (++stage == kCvAStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == P.a_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -182,7 +201,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
         // ===== weight-block producer (1-D bulk copies; the blocks are pre-packed in consumption order) =====
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = 0; t < n_tiles; ++t) {
+            const int rounds = P.w_resident ? min(n_tiles, 1) : n_tiles;
+            for (int t = 0; t < rounds; ++t) {
                 const unsigned char *src = w_packed;
                 for (int blk = 0; blk < n_kc * taps; ++blk) {
                     mbar_wait(cv_smem_u32(&bars.w_empty[stage]), phase ^ 1u, err, 102);
@@ -190,7 +210,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                     mbar_arrive_expect_tx(full, (uint32_t)P.w_stage_bytes);
                     bulk_load_1d(w_base + stage * (uint32_t)P.w_stage_bytes, src, (uint32_t)P.w_stage_bytes, full);
                     src += P.w_stage_bytes;
-                    if (++stage == kCvWStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == P.w_stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -200,47 +220,49 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t H16 = (uint32_t)P.halo * 16u;          // one chunk row of the halo tile
             const uint32_t a_lbo = H16, a_sbo = 4u * H16;
-            const uint32_t w_lbo = (uint32_t)P.npad * 16u, w_sbo = 128u;
+            const uint32_t w_lbo = (uint32_t)P.npad * 16u;
             const uint32_t w_plane = 4u * w_lbo;
+            const uint32_t a_hi_word = cv_desc_hi(a_sbo), w_hi_word = cv_desc_hi(128u);
+            const uint32_t a_lbo_f = ((a_lbo >> 4) & 0x3fffu) << 16, w_lbo_f = ((w_lbo >> 4) & 0x3fffu) << 16;
             int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int nun = min(2, u_last - (u_first + 2 * t));
-                const int set = t % P.sets;
-                const uint32_t use = (uint32_t)(t / P.sets);
+                const int nun = min(NU, u_last - (u_first + NU * t));
+                const int set = t & 1;
+                const uint32_t use = (uint32_t)(t >> 1);
                 mbar_wait(cv_smem_u32(&bars.acc_empty[set]), (use & 1u) ^ 1u, err, 103);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t acc0 = tmem_base + (uint32_t)(set * 4 * P.npad);
+                const uint32_t acc0 = tmem_base + (uint32_t)(set * 2 * NU * P.npad);
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(cv_smem_u32(&bars.a_full[as]), aph, err, 104);
                     const uint32_t a_st = a_base + as * a_stage_bytes;
                     for (int tap = 0; tap < taps; ++tap) {
-                        mbar_wait(cv_smem_u32(&bars.w_full[ws]), wph, err, 105);
+                        if (!P.w_resident || t == 0) mbar_wait(cv_smem_u32(&bars.w_full[ws]), wph, err, 105);
                         asm volatile("tcgen05.fence::after_thread_sync;");
                         const int ky = tap / P.ksize, kx = tap - ky * P.ksize;
                         const uint32_t w_st = w_base + ws * (uint32_t)P.w_stage_bytes;
+                        const uint64_t wh0 = cv_desc(w_st, w_lbo_f, w_hi_word), wl0 = cv_desc(w_st + w_plane, w_lbo_f, w_hi_word);
+                        const uint64_t wstep = (uint64_t)((2u * w_lbo) >> 4);
                         for (int un = 0; un < nun; ++un) {
 #pragma unroll
                             for (int mh = 0; mh < 2; ++mh) {
                                 const uint32_t d = acc0 + (uint32_t)((un * 2 + mh) * P.npad);
                                 const uint32_t a_hi = a_st + (uint32_t)(un * 2) * (uint32_t)P.a_unit_bytes + (uint32_t)ky * a_sbo + (uint32_t)(kx + 8 * mh) * 16u;
-                                const uint32_t a_lo = a_hi + (uint32_t)P.a_unit_bytes;
+                                const uint64_t ah0 = cv_desc(a_hi, a_lbo_f, a_hi_word);
+                                const uint64_t al0 = cv_desc(a_hi + (uint32_t)P.a_unit_bytes, a_lbo_f, a_hi_word);
+                                const uint64_t astep = (uint64_t)((2u * a_lbo) >> 4);
 #pragma unroll
                                 for (int ks = 0; ks < 2; ++ks) {
-                                    const uint64_t ah = cv_desc(a_hi + ks * 2u * a_lbo, a_lbo, a_sbo);
-                                    const uint64_t al = cv_desc(a_lo + ks * 2u * a_lbo, a_lbo, a_sbo);
-                                    const uint64_t wh = cv_desc(w_st + ks * 2u * w_lbo, w_lbo, w_sbo);
-                                    const uint64_t wl = cv_desc(w_st + w_plane + ks * 2u * w_lbo, w_lbo, w_sbo);
-                                    umma_bf16(d, ah, wh, idesc, (kc | tap | ks) != 0);
-                                    umma_bf16(d, al, wh, idesc, 1);
-                                    umma_bf16(d, ah, wl, idesc, 1);
+                                    umma_bf16(d, ah0 + ks * astep, wh0 + ks * wstep, idesc, (kc | tap | ks) != 0);
+                                    umma_bf16(d, al0 + ks * astep, wh0 + ks * wstep, idesc, 1);
+                                    umma_bf16(d, ah0 + ks * astep, wl0 + ks * wstep, idesc, 1);
                                 }
                             }
                         }
-                        umma_commit(cv_smem_u32(&bars.w_empty[ws]));      // weight block free once these MMAs retire
-                        if (++ws == kCvWStages) { ws = 0; wph ^= 1u; }
+                        if (!P.w_resident) umma_commit(cv_smem_u32(&bars.w_empty[ws]));   // weight block free once these MMAs retire
+                        if (++ws == P.w_stages) { ws = 0; wph ^= 1u; }
                     }
                     umma_commit(cv_smem_u32(&bars.a_empty[as]));          // halo chunk free
-                    if (++as == kCvAStages) { as = 0; aph ^= 1u; }
+                    if (++as == P.a_stages) { as = 0; aph ^= 1u; }
                 }
                 umma_commit(cv_smem_u32(&bars.acc_full[set]));            // accumulators of this tile complete
             }
@@ -249,11 +271,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
         // ===== epilogue: TMEM lane = GEMM row = pixel (row r: image row r/8 of the unit, pixel r%8 of the half) =====
         const int wq = warp & 3;
         const int C8 = P.cout >> 3;
+        const size_t plane = (size_t)P.B * P.Y * C8 * P.X;
         for (int t = 0; t < n_tiles; ++t) {
-            const int u0 = u_first + 2 * t;
-            const int nun = min(2, u_last - u0);
-            const int set = t % P.sets;
-            const uint32_t use = (uint32_t)(t / P.sets);
+            const int u0 = u_first + NU * t;
+            const int nun = min(NU, u_last - u0);
+            const int set = t & 1;
+            const uint32_t use = (uint32_t)(t >> 1);
             mbar_wait(cv_smem_u32(&bars.acc_full[set]), use & 1u, err, 106);
             asm volatile("tcgen05.fence::after_thread_sync;");
             for (int un = 0; un < nun; ++un) {
@@ -265,44 +288,52 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                 for (int mh = 0; mh < 2; ++mh) {
                     const int x = ux * 16 + mh * 8 + (lane & 7);
                     const bool valid = y < P.Y && x < P.X;
-                    const uint32_t col0 = (uint32_t)((set * 4 + un * 2 + mh) * P.npad);
+                    const uint32_t col0 = (uint32_t)((set * 2 * NU + un * 2 + mh) * P.npad);
+                    const size_t row0 = (((size_t)b * P.Y + y) * C8) * P.X + x;
 #pragma unroll 1
-                    for (int ch = 0; ch * 16 < P.npad; ++ch) {
-                        uint32_t v[16];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + col0 + (uint32_t)(ch * 16);
-                        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                                     : "r"(taddr));
-                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        float f[16];
+                    for (int ch = 0; ch * 32 < P.npad; ++ch) {
+                        uint32_t v[32];
+                        const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + col0 + (uint32_t)(ch * 32);
+                        if (P.npad >= 32) {
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                                         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                                           "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                                           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                                         : "r"(taddr));
+                        } else {
+                            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                                           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                                         : "r"(taddr));
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float a = __uint_as_float(v[j]) + bias_s[ch * 16 + j];
-                            if (P.act == 1) a = fmaxf(a, 0.f);
-                            else if (P.act == 2) a = 1.f / (1.f + __expf(-a));
-                            f[j] = a;
+                            for (int j = 16; j < 32; ++j) v[j] = 0u;
                         }
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                         if (valid) {
-                            if (out_split) {
 #pragma unroll
-                                for (int h = 0; h < 2; ++h) {
-                                    const int c8 = ch * 2 + h;
-                                    if (c8 < C8) {
-                                        uint4 hq, lq;
-                                        split8_bf16(f + h * 8, hq, lq);
-                                        const size_t row = (((size_t)b * P.Y + y) * C8 + c8) * P.X + x;
-                                        const size_t plane = (size_t)P.B * P.Y * C8 * P.X;
-                                        *reinterpret_cast<uint4 *>(out_split + row * 8) = hq;
-                                        *reinterpret_cast<uint4 *>(out_split + (plane + row) * 8) = lq;
+                            for (int h = 0; h < 4; ++h) {
+                                const int c8 = ch * 4 + h;
+                                if (out_split && c8 < C8) {
+                                    uint32_t hw[4], lw[4];
+#pragma unroll
+                                    for (int q = 0; q < 4; ++q) {
+                                        const int j = h * 8 + 2 * q;
+                                        cv_split2(cv_act(__uint_as_float(v[j]) + bias_s[ch * 32 + j], P.act),
+                                                  cv_act(__uint_as_float(v[j + 1]) + bias_s[ch * 32 + j + 1], P.act), hw[q], lw[q]);
                                     }
+                                    const size_t row = row0 + (size_t)c8 * P.X;
+                                    *reinterpret_cast<uint4 *>(out_split + row * 8) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                    *reinterpret_cast<uint4 *>(out_split + (plane + row) * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                                 }
                             }
                             if (out_nchw) {
 #pragma unroll
-                                for (int j = 0; j < 16; ++j) {
-                                    const int c = ch * 16 + j;
-                                    if (c < P.cout) out_nchw[(((size_t)b * P.cout + c) * P.Y + y) * P.X + x] = f[j];
+                                for (int j = 0; j < 32; ++j) {
+                                    const int c = ch * 32 + j;
+                                    if (c < P.cout)
+                                        out_nchw[(((size_t)b * P.cout + c) * P.Y + y) * P.X + x] = cv_act(__uint_as_float(v[j]) + bias_s[c], P.act);
                                 }
                             }
                         }
@@ -451,16 +482,28 @@ extern "C" int pdm_conv_tc_forward(int b, int y, int x, int cin, int cout, int k
     P.halo = 16 + ksize - 1;
     P.units_x = (x + 15) / 16; P.units_y = (y + 15) / 16;
     P.total_units = b * P.units_x * P.units_y;
-    int per = (P.total_units + 2 * kNumSMs - 1) / (2 * kNumSMs) * 2;     // even: a CTA works on pairs of units
-    if (per < 2) per = 2;
+    // two accumulator sets always (the epilogue of a tile overlaps the MMAs of the next): a tile is two 16x16 units
+    // (4 accumulators) when 8 * npad TMEM columns fit, one unit otherwise
+    P.nu = 8 * P.npad <= 512 ? 2 : 1;
+    int per = (P.total_units + P.nu * kNumSMs - 1) / (P.nu * kNumSMs) * P.nu;
+    if (per < P.nu) per = P.nu;
     P.units_per_cta = per;
     const int grid = (P.total_units + per - 1) / per;
     P.a_unit_bytes = P.halo * 4 * P.halo * 16;
     P.w_stage_bytes = 2 * 4 * P.npad * 16;
-    P.sets = 8 * P.npad <= 512 ? 2 : 1;
-    int cols = 4 * P.npad * P.sets, pw = 32;
+    int cols = 4 * P.nu * P.npad, pw = 32;
     while (pw < cols) pw <<= 1;
     P.tmem_cols = pw;
+    // shared memory: halo ring (2 stages when a tile has two units, else 3), the rest for weight blocks;
+    // if every block of the layer fits they stay resident
+    const int a_stage = 2 * P.nu * P.a_unit_bytes;
+    const int n_blocks = (cin / 32) * ksize * ksize;
+    P.a_stages = P.nu == 2 ? 2 : 3;
+    int w_fit = (kCvSmemBudget - P.a_stages * a_stage) / P.w_stage_bytes;
+    if (w_fit < 2 && P.a_stages > 2) { P.a_stages = 2; w_fit = (kCvSmemBudget - P.a_stages * a_stage) / P.w_stage_bytes; }
+    if (w_fit < 2) return fail(PDM_ERR_UNSUPPORTED, "conv_tc_forward: operands do not fit in shared memory");
+    P.w_resident = (w_fit >= n_blocks && n_blocks <= kCvMaxWStages) ? 1 : 0;
+    P.w_stages = P.w_resident ? n_blocks : (w_fit < 8 ? w_fit : 8);
 
     CUtensorMap tmap;
     const cuuint64_t gdim[5] = {(cuuint64_t)x * 8, (cuuint64_t)(cin / 8), (cuuint64_t)y, (cuuint64_t)b, 2};
@@ -473,7 +516,7 @@ extern "C" int pdm_conv_tc_forward(int b, int y, int x, int cin, int cout, int k
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (cr != CUDA_SUCCESS) return fail(PDM_ERR_INVALID_ARG, "conv_tc_forward: cuTensorMapEncodeTiled failed (%d)", (int)cr);
 
-    const size_t smem = (size_t)kCvAStages * 4 * P.a_unit_bytes + (size_t)kCvWStages * P.w_stage_bytes + 128;
+    const size_t smem = (size_t)P.a_stages * a_stage + (size_t)P.w_stages * P.w_stage_bytes + 128;
     if (int rc = ensure_dynamic_smem((const void *)conv_tc_kernel, smem)) return rc;
     conv_tc_kernel<<<grid, kCvThreads, smem, (cudaStream_t)stream>>>(tmap, P, (const unsigned char *)w_packed, bias,
                                                                     (__nv_bfloat16 *)out_split, out_nchw, conv_err_word());

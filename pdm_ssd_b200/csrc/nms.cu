@@ -85,17 +85,19 @@ __device__ float bev_overlap(const float *a, const float *b) {
     float sx = 0.f, sy = 0.f;
     for (int i = 0; i < 4; ++i)
         for (int j = 0; j < 4; ++j)
-            if (seg_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], pts[cnt])) {
+            if (cnt < 16 && seg_intersection(ca[i + 1], ca[i], cb[j + 1], cb[j], pts[cnt])) {
                 sx = sx + pts[cnt].x;
                 sy = sy + pts[cnt].y;
                 ++cnt;
             }
     for (int k = 0; k < 4; ++k) {
-        if (inside_with_margin(a, cb[k])) {
+        // (the reference's 16-slot array can overflow when margin corners add to 8 edge crossings,
+        //  iou3d_nms_kernel.cu:150-172; such points are dropped here instead of written past the end)
+        if (cnt < 16 && inside_with_margin(a, cb[k])) {
             sx = sx + cb[k].x; sy = sy + cb[k].y;
             pts[cnt++] = cb[k];
         }
-        if (inside_with_margin(b, ca[k])) {
+        if (cnt < 16 && inside_with_margin(b, ca[k])) {
             sx = sx + ca[k].x; sy = sy + ca[k].y;
             pts[cnt++] = ca[k];
         }
@@ -130,6 +132,23 @@ __device__ __forceinline__ float bev_iou(const float *a, const float *b) {
     return s / fmaxf(sa + sb - s, kNmsEps);
 }
 
+// axis-aligned BEV IoU, heading ignored (iou_normal, iou3d_nms_kernel.cu:341-352)
+__device__ __forceinline__ float bev_iou_normal(const float *a, const float *b) {
+    const float left = fmaxf(a[0] - a[3] / 2, b[0] - b[3] / 2), right = fminf(a[0] + a[3] / 2, b[0] + b[3] / 2);
+    const float top = fmaxf(a[1] - a[4] / 2, b[1] - b[4] / 2), bottom = fminf(a[1] + a[4] / 2, b[1] + b[4] / 2);
+    const float width = fmaxf(right - left, 0.f), height = fmaxf(bottom - top, 0.f);
+    const float inter = width * height;
+    return inter / fmaxf(a[3] * a[4] + b[3] * b[4] - inter, kNmsEps);
+}
+
+// overlap of box i of `a` with box i of `b` (paired_boxes_overlap_kernel / boxes_aligned_overlap_kernel,
+// iou3d_nms_kernel.cu:251-277)
+__global__ void __launch_bounds__(256)
+paired_bev_kernel(int n, const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ ans) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) ans[i] = bev_overlap(a + (size_t)i * 7, b + (size_t)i * 7);
+}
+
 // pairwise IoU (iou3d_nms_kernel.cu:279-293) or overlap area (:236-249): ans[i, j] = f(a_i, b_j)
 template <bool IOU>
 __global__ void __launch_bounds__(256)
@@ -141,6 +160,8 @@ pair_bev_kernel(int na, const float *__restrict__ a, int nb, const float *__rest
 }
 
 // mask[f, i, w] bit t  <=>  IoU(box i, box 64w + t) > thresh, for 64w + t > i.  Upper-triangular tiles.
+// NORMAL: axis-aligned IoU (nms_normal_kernel, iou3d_nms_kernel.cu:355-398) instead of the rotated one.
+template <bool NORMAL>
 __global__ void __launch_bounds__(kTile)
 nms_mask_kernel(int k, int words, const int *__restrict__ counts, float thresh, const float *__restrict__ boxes,
                 unsigned long long *__restrict__ mask) {
@@ -166,6 +187,10 @@ nms_mask_kernel(int k, int words, const int *__restrict__ counts, float thresh, 
                 const float *ob = tile + t * 7;
                 const float ddx = ob[0] - me[0], ddy = ob[1] - me[1];
                 const float rr = my_r + 0.5f * sqrtf(ob[3] * ob[3] + ob[4] * ob[4]) * 1.001f + 0.1f;
+                if (NORMAL) {
+                    if (bev_iou_normal(me, ob) > thresh) bits |= 1ull << t;
+                    continue;
+                }
                 if (thresh >= 0.f && ddx * ddx + ddy * ddy > rr * rr) continue;
                 if (bev_iou(me, ob) > thresh) bits |= 1ull << t;
             }
@@ -174,8 +199,9 @@ nms_mask_kernel(int k, int words, const int *__restrict__ counts, float thresh, 
     if (i < k) mask[((size_t)f * k + i) * words + ct] = bits;
 }
 
-// Greedy pass, one warp per frame (iou3d_nms.cpp:159-176).  Lane l owns words l and l+32 of the
-// "removed" set (up to 4096 boxes); mask rows are prefetched a few iterations ahead.
+// Greedy pass, one warp per frame (iou3d_nms.cpp:159-176).  Lane l owns words l, l+32, ... of the "removed" set
+// (WPL words per lane: 2 covers 4096 boxes, 8 covers 16 384); mask rows are prefetched a few iterations ahead.
+template <int WPL>
 __global__ void __launch_bounds__(32)
 nms_sweep_kernel(int k, int words, const int *__restrict__ counts, const unsigned long long *__restrict__ mask,
                  int *__restrict__ keep, int *__restrict__ num_keep) {
@@ -183,31 +209,40 @@ nms_sweep_kernel(int k, int words, const int *__restrict__ counts, const unsigne
     const int n = counts ? min(__ldg(counts + f), k) : k;
     const unsigned long long *fm = mask + (size_t)f * k * words;
     int *fk = keep + (size_t)f * k;
-    unsigned long long rem0 = 0ull, rem1 = 0ull;
-    constexpr int PF = 4;
-    unsigned long long r0[PF], r1[PF];
+    unsigned long long rem[WPL];
 #pragma unroll
-    for (int q = 0; q < PF; ++q) {
-        r0[q] = (q < n && lane < words) ? __ldg(fm + (size_t)q * words + lane) : 0ull;
-        r1[q] = (q < n && lane + 32 < words) ? __ldg(fm + (size_t)q * words + lane + 32) : 0ull;
-    }
+    for (int w = 0; w < WPL; ++w) rem[w] = 0ull;
+    constexpr int PF = WPL <= 2 ? 4 : 2;
+    unsigned long long r[PF][WPL];
+#pragma unroll
+    for (int q = 0; q < PF; ++q)
+#pragma unroll
+        for (int w = 0; w < WPL; ++w)
+            r[q][w] = (q < n && lane + 32 * w < words) ? __ldg(fm + (size_t)q * words + lane + 32 * w) : 0ull;
     int kept = 0;
     for (int base = 0; base < n; base += PF) {
 #pragma unroll
         for (int q = 0; q < PF; ++q) {
             const int i = base + q;
-            const unsigned long long m0 = r0[q], m1 = r1[q];
+            unsigned long long m[WPL];
             const int nxt = i + PF;  // refill this slot for iteration i + PF
-            r0[q] = (nxt < n && lane < words) ? __ldg(fm + (size_t)nxt * words + lane) : 0ull;
-            r1[q] = (nxt < n && lane + 32 < words) ? __ldg(fm + (size_t)nxt * words + lane + 32) : 0ull;
+#pragma unroll
+            for (int w = 0; w < WPL; ++w) {
+                m[w] = r[q][w];
+                r[q][w] = (nxt < n && lane + 32 * w < words) ? __ldg(fm + (size_t)nxt * words + lane + 32 * w) : 0ull;
+            }
             if (i < n) {
-                const int w = i >> 6;
-                const unsigned long long word = __shfl_sync(0xffffffffu, w < 32 ? rem0 : rem1, w & 31);
+                const int wi = i >> 6;
+                unsigned long long mine = rem[0];
+#pragma unroll
+                for (int w = 1; w < WPL; ++w)
+                    if ((wi >> 5) == w) mine = rem[w];
+                const unsigned long long word = __shfl_sync(0xffffffffu, mine, wi & 31);
                 if (!((word >> (i & 63)) & 1ull)) {   // warp-uniform
                     if (lane == 0) fk[kept] = i;
                     ++kept;
-                    rem0 |= m0;
-                    rem1 |= m1;
+#pragma unroll
+                    for (int w = 0; w < WPL; ++w) rem[w] |= m[w];
                 }
             }
         }
@@ -242,13 +277,24 @@ int pdm_boxes_overlap_bev(int na, const float *boxes_a, int nb, const float *box
     return pair_bev(false, na, boxes_a, nb, boxes_b, ans_overlap, stream);
 }
 
-int pdm_nms_bev_batched(int frames, int k, const float *boxes, const int *counts, float thresh, int *keep,
-                        int *num_keep, void *stream) {
+int pdm_boxes_overlap_bev_paired(int n, const float *boxes_a, const float *boxes_b, float *ans_overlap, void *stream) {
+    using namespace pdm;
+    if (n < 0) return fail(PDM_ERR_INVALID_ARG, "boxes_overlap_bev_paired: negative size");
+    if (n == 0) return PDM_OK;
+    if (!boxes_a || !boxes_b || !ans_overlap) return fail(PDM_ERR_INVALID_ARG, "boxes_overlap_bev_paired: null pointer");
+    paired_bev_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(n, boxes_a, boxes_b, ans_overlap);
+    count_launch();
+    PDM_CHECK_LAUNCH("boxes_overlap_bev_paired");
+    return PDM_OK;
+}
+
+static int nms_batched(bool normal, int frames, int k, const float *boxes, const int *counts, float thresh, int *keep,
+                       int *num_keep, void *stream) {
     using namespace pdm;
     if (frames < 0 || k < 0) return fail(PDM_ERR_INVALID_ARG, "nms_bev_batched: negative size");
     if (frames == 0) return PDM_OK;
     if (!keep || !num_keep || (k > 0 && !boxes)) return fail(PDM_ERR_INVALID_ARG, "nms_bev_batched: null pointer");
-    if (k > 4096) return fail(PDM_ERR_UNSUPPORTED, "nms_bev_batched: at most 4096 boxes per frame (got %d)", k);
+    if (k > 16384) return fail(PDM_ERR_UNSUPPORTED, "nms_bev_batched: at most 16384 boxes per frame (got %d)", k);
     if (frames > 65535) return fail(PDM_ERR_UNSUPPORTED, "nms_bev_batched: too many frames");
     cudaStream_t st = (cudaStream_t)stream;
     const int words = (k + kTile - 1) / kTile;
@@ -257,14 +303,26 @@ int pdm_nms_bev_batched(int frames, int k, const float *boxes, const int *counts
         mask = static_cast<unsigned long long *>(stream_scratch(st, (size_t)frames * k * words * sizeof(unsigned long long)));
         if (!mask) return PDM_ERR_INVALID_ARG;
         dim3 grid(words, words, frames);
-        nms_mask_kernel<<<grid, kTile, 0, st>>>(k, words, counts, thresh, boxes, mask);
+        if (normal) nms_mask_kernel<true><<<grid, kTile, 0, st>>>(k, words, counts, thresh, boxes, mask);
+        else nms_mask_kernel<false><<<grid, kTile, 0, st>>>(k, words, counts, thresh, boxes, mask);
         count_launch();
         PDM_CHECK_LAUNCH("nms_bev_batched(mask)");
     }
-    nms_sweep_kernel<<<frames, 32, 0, st>>>(k, words, counts, mask, keep, num_keep);
+    if (words <= 64) nms_sweep_kernel<2><<<frames, 32, 0, st>>>(k, words, counts, mask, keep, num_keep);
+    else nms_sweep_kernel<8><<<frames, 32, 0, st>>>(k, words, counts, mask, keep, num_keep);
     count_launch();
     PDM_CHECK_LAUNCH("nms_bev_batched(sweep)");
     return PDM_OK;
+}
+
+int pdm_nms_bev_batched(int frames, int k, const float *boxes, const int *counts, float thresh, int *keep,
+                        int *num_keep, void *stream) {
+    return nms_batched(false, frames, k, boxes, counts, thresh, keep, num_keep, stream);
+}
+
+int pdm_nms_normal_batched(int frames, int k, const float *boxes, const int *counts, float thresh, int *keep,
+                           int *num_keep, void *stream) {
+    return nms_batched(true, frames, k, boxes, counts, thresh, keep, num_keep, stream);
 }
 
 }  // extern "C"

@@ -3,8 +3,8 @@
 Constructor and forward follow the slot's contract (detector3d_template.py:85-95): built as
 `PDMNeck(model_cfg=..., grid_size=...)`, exposes `num_bev_features`, `forward(batch_dict)` reads
 `point_coords` / `point_features` / `batch_size` and writes `spatial_features (B,C,Y,X)`.
-The compute is one C-ABI call (`pdm_neck_forward`, csrc/pdm_neck.cu); the per-centre SH
-coefficients come from an ordinary `nn.Linear` (a plain library GEMM).
+The compute is one C-ABI call (`pdm_neck_forward[_split]`, csrc/pdm_neck.cu); the per-centre SH
+coefficients come from `pdm_linear_rows` (csrc/point_head.cu) at inference, from `nn.Linear` otherwise.
 """
 import ctypes
 
@@ -22,9 +22,11 @@ def _get(cfg, key, default=None):
 
 
 def neck_forward(point_coords, point_features, coef, batch_size, point_cloud_range, voxel_size, grid,
-                 dilation=(1, 1, 1), sh_degree=2, sigma=0.8, eps=1e-6, return_debug=False):
-    """Functional form.  All tensors CUDA fp32 contiguous.  Returns spatial_features (B,C,Y,X)
-    [, keys (P,K) int32, weights (P,K) fp32]."""
+                 dilation=(1, 1, 1), sh_degree=2, sigma=0.8, eps=1e-6, return_debug=False, output="nchw"):
+    """Functional form.  All tensors CUDA fp32 contiguous.
+    output="nchw": returns spatial_features (B,C,Y,X) [, keys (P,K) int32, weights (P,K) fp32];
+    output="split": returns the map as a `conv_tc.SplitAct` (what the tensor-core convolutions read);
+    output="both": (spatial_features, SplitAct)."""
     lib = _lib.load()
     for name, t in (("point_coords", point_coords), ("point_features", point_features), ("coef", coef)):
         if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
@@ -35,22 +37,51 @@ def neck_forward(point_coords, point_features, coef, batch_size, point_cloud_ran
         raise RuntimeError("shape mismatch: point_coords %s, coef %s" % (tuple(point_coords.shape), tuple(coef.shape)))
     X, Y, Z = (int(g) for g in grid)
     K = int(np.prod([2 * int(k) + 1 for k in dilation]))
-    out = torch.empty((batch_size, C, Y, X), dtype=torch.float32, device=point_features.device)
+    dev = point_features.device
+    f3, i3 = ctypes.c_float * 3, ctypes.c_int * 3
+    cfg = (f3(*[float(v) for v in point_cloud_range[:3]]), f3(*[float(v) for v in voxel_size]),
+           i3(X, Y, Z), i3(*[int(k) for k in dilation]), int(sh_degree), float(sigma), float(eps))
+    if output != "nchw":
+        if return_debug:
+            raise RuntimeError("return_debug needs output='nchw'")
+        from .conv_tc import SplitAct
+        split = SplitAct.empty(batch_size, C, Y, X, dev)
+        out = torch.empty((batch_size, C, Y, X), dtype=torch.float32, device=dev) if output == "both" else None
+        with torch.cuda.device(dev):
+            rc = lib.pdm_neck_forward_split(
+                int(batch_size), P, C, point_coords.data_ptr(), point_features.data_ptr(), coef.data_ptr(), *cfg,
+                out.data_ptr() if out is not None else None, split.data.data_ptr(),
+                torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(rc, "pdm_neck_forward_split")
+        return (out, split) if output == "both" else split
+    out = torch.empty((batch_size, C, Y, X), dtype=torch.float32, device=dev)
     keys = wts = None
     if return_debug:
         keys = torch.empty((P, K), dtype=torch.int32, device=out.device)
         wts = torch.empty((P, K), dtype=torch.float32, device=out.device)
-    f3, i3 = ctypes.c_float * 3, ctypes.c_int * 3
     with torch.cuda.device(out.device):
         rc = lib.pdm_neck_forward(
-            int(batch_size), P, C, point_coords.data_ptr(), point_features.data_ptr(), coef.data_ptr(),
-            f3(*[float(v) for v in point_cloud_range[:3]]), f3(*[float(v) for v in voxel_size]),
-            i3(X, Y, Z), i3(*[int(k) for k in dilation]), int(sh_degree), float(sigma), float(eps),
+            int(batch_size), P, C, point_coords.data_ptr(), point_features.data_ptr(), coef.data_ptr(), *cfg,
             out.data_ptr(), keys.data_ptr() if keys is not None else None,
             wts.data_ptr() if wts is not None else None,
             torch.cuda.current_stream(out.device).cuda_stream)
     _lib.check(rc, "pdm_neck_forward")
     return (out, keys, wts) if return_debug else out
+
+
+def linear_rows(x, weight, bias=None):
+    """nn.Linear for a handful of outputs per row on our kernel (csrc/point_head.cu): x (P,C) -> (P,nout)."""
+    if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+        raise RuntimeError("linear_rows needs a contiguous CUDA float32 input")
+    P, C = x.shape
+    w = weight.detach().contiguous()
+    b = bias.detach().contiguous() if bias is not None else None
+    out = torch.empty((P, w.shape[0]), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = _lib.load().pdm_linear_rows(P, C, w.shape[0], x.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None,
+                                         out.data_ptr(), torch.cuda.current_stream(x.device).cuda_stream)
+    _lib.check(rc, "pdm_linear_rows")
+    return out
 
 
 class PDMNeck(nn.Module):
@@ -74,9 +105,19 @@ class PDMNeck(nn.Module):
     def forward(self, batch_dict):
         feats = batch_dict["point_features"].contiguous()
         coords = batch_dict["point_coords"].contiguous()
-        coef = self.coef(feats).contiguous()
-        batch_dict["spatial_features"] = neck_forward(
-            coords, feats, coef, int(batch_dict["batch_size"]), self.point_cloud_range, self.voxel_size,
-            self.grid_size, self.dilation, self.sh_degree, self.sigma, self.eps)
+        # inference on a GPU: the coefficient Linear runs on our kernel and the map is written in the layout the
+        # tensor-core convolutions read; `spatial_features` (fp32, the slot's contract) is written too unless the
+        # caller says nobody will read it (batch_dict['pdm_fused_dense'], set by the PDMSSD detector)
+        native = feats.is_cuda and not self.training and not torch.is_grad_enabled() and feats.dtype == torch.float32
+        coef = linear_rows(feats, self.coef.weight, self.coef.bias) if native and self.coef.out_features <= 16 \
+            else self.coef(feats).contiguous()
+        args = (coords, feats, coef, int(batch_dict["batch_size"]), self.point_cloud_range, self.voxel_size,
+                self.grid_size, self.dilation, self.sh_degree, self.sigma, self.eps)
+        if native and self.num_bev_features % 8 == 0 and batch_dict.get("pdm_fused_dense", False):
+            batch_dict["spatial_features_split"] = neck_forward(*args, output="split")
+        elif native and self.num_bev_features % 8 == 0 and batch_dict.get("pdm_want_split", False):
+            batch_dict["spatial_features"], batch_dict["spatial_features_split"] = neck_forward(*args, output="both")
+        else:
+            batch_dict["spatial_features"] = neck_forward(*args)
         batch_dict["spatial_features_stride"] = 1
         return batch_dict

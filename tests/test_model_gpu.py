@@ -76,7 +76,7 @@ def test_detector_end_to_end_shapes_determinism_and_frame_independence():
     out = model({"batch_size": 4, "points": pts})
     det = out["detections"]
     assert det.shape == (4, 100, 9) and torch.isfinite(det).all()
-    assert out["spatial_features"].shape == (4, 128, 200, 176)
+    assert out["spatial_features_split"].data.shape == (2, 4, 200, 16, 176, 8)      # the BEV map in the convs' split layout
     assert out["batch_box_preds"].shape == (4 * 256, 7) and out["batch_cls_preds"].shape == (4 * 256, 3)
     num = out["num_detections"].cpu()
     assert (num >= 1).all() and (num <= 100).all()
@@ -85,15 +85,19 @@ def test_detector_end_to_end_shapes_determinism_and_frame_independence():
         assert (d[:, 8] >= 1).all() and (d[:, 8] <= 3).all() and (d[:, 7] >= 0.1).all()
         assert (det[f, num[f]:] == 0).all()                 # fixed shape, zero padded
     assert (det[:, :-1, 7] >= det[:, 1:, 7]).all()          # sorted by score
-    # same boxes as pcdet's per-frame post-processing (detector3d_template.py:199-254) on the head outputs
-    from pdm_ssd_b200 import model_nms_utils
-    nms_cfg = default_cfg().POST_PROCESSING.NMS_CONFIG
-    for f in range(4):
-        sc, _ = out["batch_cls_preds"][f * 256:(f + 1) * 256].max(dim=1)
-        bx = out["batch_box_preds"][f * 256:(f + 1) * 256]
-        sel, ssc = model_nms_utils.class_agnostic_nms(sc, bx, nms_cfg, score_thresh=0.1)
-        assert len(sel) == num[f]
-        assert torch.equal(bx[sel], det[f, :num[f], :7]) and torch.equal(ssc, det[f, :num[f], 7])
+    # same boxes as pcdet's per-frame post-processing (detector3d_template.py:199-254): the REFERENCE's own
+    # class_agnostic_nms (model_nms_utils.py:6-25, vendored by oracle/build_ref.py) running on our iou3d_nms extension
+    import build_ref
+    from pdm_ssd_b200 import iou3d_nms_cuda
+    ns = build_ref.load_reference_tree("refpy_on_ours", ours, iou3d_nms_cuda)
+    if ns is not None:
+        nms_cfg = default_cfg().POST_PROCESSING.NMS_CONFIG
+        for f in range(4):
+            sc, _ = out["batch_cls_preds"][f * 256:(f + 1) * 256].max(dim=1)
+            bx = out["batch_box_preds"][f * 256:(f + 1) * 256]
+            sel, ssc = ns.model_nms_utils.class_agnostic_nms(sc, bx, nms_cfg, score_thresh=0.1)
+            assert len(sel) == num[f]
+            assert torch.equal(bx[sel], det[f, :num[f], :7]) and torch.equal(ssc, det[f, :num[f], 7])
     again = model({"batch_size": 4, "points": pts})["detections"]
     assert torch.equal(det, again)                            # deterministic end to end
     # sharding by frame (what the multi-GPU path does) reproduces the batched result

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import oracle
-from pdm_ssd_b200 import iou3d_nms_cuda as ours, iou3d_nms_utils as utils, model_nms_utils, synthetic
+from pdm_ssd_b200 import iou3d_nms_cuda as ours, iou3d_nms_utils as utils, pointnet2_batch_cuda as ours_pn2, synthetic
 from pdm_ssd_b200.backbone import AttrDict
 from test_nms_cpu import assert_keep_lists_agree
 
@@ -28,6 +28,24 @@ def ref_nms():
     return build_ref.load_ref_nms()
 
 
+@pytest.fixture(scope="module")
+def refpy():
+    """The reference's own iou3d_nms_utils.py / model_nms_utils.py (vendored unchanged by oracle/build_ref.py)
+    running on OUR extension module."""
+    import build_ref
+    ns = build_ref.load_reference_tree("refpy_on_ours", ours_pn2, ours)
+    if ns is None:
+        pytest.skip("reference python files not vendored (oracle/_ref/py)")
+    return ns
+
+
+def our_iou_bev(a, b):
+    """(Na,7), (Nb,7) -> (Na,Nb) through the extension-level entry (caller allocates, iou3d_nms_utils.py:41-42)."""
+    out = torch.zeros((a.shape[0], b.shape[0]), dtype=torch.float32, device=DEV)
+    ours.boxes_iou_bev_gpu(a.contiguous(), b.contiguous(), out)
+    return out
+
+
 def our_keep(boxes, thresh):
     b = _t(boxes)
     keep = torch.zeros(len(boxes), dtype=torch.int64)
@@ -40,7 +58,7 @@ def test_golden(path):
     g = np.load(path)
     boxes, thresh = g["boxes"], float(g["thresh"])
     m = g["iou"].shape[0]
-    iou = utils.boxes_iou_bev(_t(boxes[:m]), _t(boxes[:m])).cpu().numpy()
+    iou = our_iou_bev(_t(boxes[:m]), _t(boxes[:m])).cpu().numpy()
     np.testing.assert_allclose(iou, g["iou"], rtol=0, atol=1e-5)
     ovl = torch.zeros((m, m), device=DEV)
     ours.boxes_overlap_bev_gpu(_t(boxes[:m]), _t(boxes[:m]), ovl)
@@ -72,7 +90,7 @@ def test_iou_vs_oracle_and_reference(ref_nms):
     a = synthetic.random_boxes(333, seed=21, clusters=15)
     b = synthetic.random_boxes(257, seed=22, clusters=15)
     b[:100] = a[:100] + np.random.default_rng(0).normal(0, 0.05, (100, 7)).astype(np.float32)
-    got = utils.boxes_iou_bev(_t(a), _t(b)).cpu().numpy()
+    got = our_iou_bev(_t(a), _t(b)).cpu().numpy()
 
     def close(x, y, atol):
         # The construction is ill-conditioned for nearly coincident boxes (a straddle test or the 1e-2
@@ -88,9 +106,10 @@ def test_iou_vs_oracle_and_reference(ref_nms):
     assert (got > 0.3).sum() > 50
 
 
-def test_iou3d_matches_definition():
+def test_iou3d_matches_definition(refpy):
+    """The reference's boxes_iou3d_gpu (iou3d_nms_utils.py:47-82) on our boxes_overlap_bev_gpu."""
     a = synthetic.random_boxes(200, seed=31, clusters=10)
-    got = utils.boxes_iou3d_gpu(_t(a), _t(a)).cpu().numpy()
+    got = refpy.iou3d_nms_utils.boxes_iou3d_gpu(_t(a), _t(a)).cpu().numpy()
     assert np.allclose(np.diag(got), 1.0, atol=1e-4)
     bev = oracle.boxes_iou_bev(a, a)
     assert ((got > 0) <= (bev > 0)).all()
@@ -116,8 +135,10 @@ def test_batched_counts_padding_and_frames():
     assert np.array_equal(keep2[0, :num2[0]].cpu().numpy(), oracle.nms_bev(boxes[0], 0.2))
 
 
-def test_utils_nms_gpu_reference_semantics():
-    """iou3d_nms_utils.nms_gpu: unsorted boxes + scores, pre_maxsize (iou3d_nms_utils.py:120-135)."""
+def test_utils_nms_gpu_reference_semantics(refpy):
+    """The reference's iou3d_nms_utils.nms_gpu (iou3d_nms_utils.py:120-135) on our extension: unsorted boxes +
+    scores, pre_maxsize."""
+    utils = refpy.iou3d_nms_utils
     n = 700
     boxes = synthetic.random_boxes(n, seed=51, clusters=25)
     scores = np.random.default_rng(51).uniform(0, 1, n).astype(np.float32)
@@ -127,7 +148,8 @@ def test_utils_nms_gpu_reference_semantics():
     assert np.array_equal(sel.cpu().numpy(), want)
 
 
-def test_class_agnostic_and_batched_agree():
+def test_class_agnostic_and_batched_agree(refpy):
+    model_nms_utils = refpy.model_nms_utils
     F, M = 4, 1024
     rng = np.random.default_rng(61)
     boxes = np.stack([synthetic.random_boxes(M, seed=60 + f, clusters=30) for f in range(F)])
@@ -168,6 +190,49 @@ def test_errors():
     with pytest.raises(RuntimeError):
         ours.boxes_iou_bev_gpu(torch.zeros(3, 7), torch.zeros(3, 7), torch.zeros(3, 3))      # CPU tensors
     with pytest.raises(RuntimeError):
-        ours.nms_bev_batched(torch.zeros((1, 5000, 7), device=DEV), None, 0.1,
-                             torch.empty((1, 5000), dtype=torch.int32, device=DEV),
-                             torch.empty((1,), dtype=torch.int32, device=DEV))               # k > 4096
+        ours.nms_bev_batched(torch.zeros((1, 20000, 7), device=DEV), None, 0.1,
+                             torch.empty((1, 20000), dtype=torch.int32, device=DEV),
+                             torch.empty((1,), dtype=torch.int32, device=DEV))               # k > 16384
+
+
+def test_more_than_4096_boxes_and_normal_nms(ref_nms):
+    """NMS_PRE_MAXSIZE up to 9000 in stock pcdet configs: the wide sweep (8 mask words per lane), and the
+    axis-aligned variant nms_normal_gpu (iou3d_nms.cpp:186-233), against the CPU oracle / the reference kernels."""
+    n = 9000
+    boxes = synthetic.random_boxes(n, seed=77, clusters=200)
+    got = our_keep(boxes, 0.3)
+    want = oracle.nms_bev(boxes, 0.3)
+    assert np.array_equal(got, want)
+    if ref_nms is None:
+        pytest.skip("oracle/_ref/iou3d_nms_cuda_ref.so not built")
+    for m in (700, 5000):
+        b = _t(boxes[:m])
+        k1, k2 = torch.zeros(m, dtype=torch.int64), torch.zeros(m, dtype=torch.int64)
+        n1, n2 = ours.nms_normal_gpu(b, k1, 0.2), ref_nms.nms_normal_gpu(b, k2, 0.2)
+        assert n1 == n2 and torch.equal(k1[:n1], k2[:n2])
+    a, bb = _t(boxes[:600]), _t(boxes[300:900])
+    o1 = torch.zeros(600, 1, device=DEV)
+    o2 = torch.zeros(600, 1, device=DEV)
+    ours.paired_boxes_overlap_bev_gpu(a, bb, o1)
+    ref_nms.paired_boxes_overlap_bev_gpu(a, bb, o2)
+    assert torch.equal(o1, o2)
+    ours.boxes_aligned_overlap_bev_gpu(a, bb, o1)
+    ref_nms.boxes_aligned_overlap_bev_gpu(a, bb, o2)
+    assert torch.equal(o1, o2)
+
+
+def test_batched_multi_classes_nms_matches_reference_loop(refpy):
+    """batched_multi_classes_nms_gpu against the reference's multi_classes_nms (model_nms_utils.py:28-66) per frame."""
+    F, M, C = 3, 800, 3
+    rng = np.random.default_rng(5)
+    boxes = np.stack([synthetic.random_boxes(M, seed=90 + f, clusters=25) for f in range(F)])
+    cls = rng.uniform(0, 1, (F, M, C)).astype(np.float32)
+    cfg = AttrDict(NMS_TYPE="nms_gpu", NMS_THRESH=0.1, NMS_PRE_MAXSIZE=512, NMS_POST_MAXSIZE=40)
+    sel, num = utils.batched_multi_classes_nms_gpu(_t(boxes), _t(cls), 0.1, 512, 40, score_thresh=0.25)
+    for f in range(F):
+        sc, lb, bx = refpy.model_nms_utils.multi_classes_nms(_t(cls[f]), _t(boxes[f]), cfg, score_thresh=0.25)
+        mine_sc, mine_lb, mine_bx = [], [], []
+        for k in range(C):
+            idx = sel[f, k, :int(num[f, k])]
+            mine_sc.append(_t(cls[f])[idx, k]); mine_lb.append(torch.full_like(idx, k)); mine_bx.append(_t(boxes[f])[idx])
+        assert torch.equal(torch.cat(mine_sc), sc) and torch.equal(torch.cat(mine_lb), lb) and torch.equal(torch.cat(mine_bx), bx)
