@@ -55,6 +55,8 @@ struct ConvTCParams {
     int w_resident;      // every weight block has its own slot: loaded once per CTA, never released
     int act;             // 0 none, 1 relu, 2 sigmoid
     int tmem_cols;
+    int debug;           // PDM_CONV_DEBUG (measurement only, results wrong): 1 halo loads only while the ring fills,
+                         // 2 same for weight blocks, 4 no global stores in the epilogue
 };
 
 __device__ __forceinline__ uint32_t cv_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,6 +119,16 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a converged warp.  The role loops below stay warp-uniform (every lane waits on the barriers and
+// computes the descriptors, which therefore live in uniform registers) and only the issuing instruction sits
+// under this predicate; a loop that is entered by `lane == 0` alone makes ptxas wrap every tcgen05.mma / TMA
+// instruction in an ELECT ... BRA.U.ANY uniformisation loop plus R2UR moves (measured: ~85 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 struct __align__(8) ConvBarriers {
     uint64_t a_full[kCvMaxAStages], a_empty[kCvMaxAStages];
     uint64_t w_full[kCvMaxWStages], w_empty[kCvMaxWStages];
@@ -176,7 +188,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
 
     if (warp == 0) {
         // ===== halo-tile producer (TMA tensor loads) =====
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int u0 = u_first + NU * t;
@@ -184,14 +196,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(cv_smem_u32(&bars.a_empty[stage]), phase ^ 1u, err, 101);
                     const uint32_t full = cv_smem_u32(&bars.a_full[stage]);
-                    mbar_arrive_expect_tx(full, (uint32_t)(nun * 2 * P.a_unit_bytes));
+                    if ((P.debug & 1) && (t * n_kc + kc) >= P.a_stages) {
+                        if (elect_one()) mbar_arrive(full);
+                        __syncwarp();
+                        if (++stage == P.a_stages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
+                    if (elect_one()) mbar_arrive_expect_tx(full, (uint32_t)(nun * 2 * P.a_unit_bytes));
+                    __syncwarp();
                     for (int un = 0; un < nun; ++un) {
                         const int u = u0 + un;
                         const int ux = u % P.units_x, r = u / P.units_x;
                         const int uy = r % P.units_y, b = r / P.units_y;
-                        for (int pl = 0; pl < 2; ++pl)
-                            tma_load_5d(a_base + stage * a_stage_bytes + (uint32_t)((un * 2 + pl) * P.a_unit_bytes), &tmap_in, full,
-                                        (ux * 16 - pad) * 8, kc * 4, uy * 16 - pad, b, pl);
+                        const uint32_t dst = a_base + stage * a_stage_bytes + (uint32_t)(un * 2 * P.a_unit_bytes);
+                        if (elect_one()) {
+                            tma_load_5d(dst, &tmap_in, full, (ux * 16 - pad) * 8, kc * 4, uy * 16 - pad, b, 0);
+                            tma_load_5d(dst + (uint32_t)P.a_unit_bytes, &tmap_in, full, (ux * 16 - pad) * 8, kc * 4, uy * 16 - pad, b, 1);
+                        }
+                        __syncwarp();
                     }
                     if (++stage == P.a_stages) { stage = 0; phase ^= 1u; }
                 }
@@ -199,7 +221,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
         }
     } else if (warp == 1) {
         // ===== weight-block producer (1-D bulk copies; the blocks are pre-packed in consumption order) =====
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             const int rounds = P.w_resident ? min(n_tiles, 1) : n_tiles;
             for (int t = 0; t < rounds; ++t) {
@@ -207,8 +229,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                 for (int blk = 0; blk < n_kc * taps; ++blk) {
                     mbar_wait(cv_smem_u32(&bars.w_empty[stage]), phase ^ 1u, err, 102);
                     const uint32_t full = cv_smem_u32(&bars.w_full[stage]);
-                    mbar_arrive_expect_tx(full, (uint32_t)P.w_stage_bytes);
-                    bulk_load_1d(w_base + stage * (uint32_t)P.w_stage_bytes, src, (uint32_t)P.w_stage_bytes, full);
+                    if ((P.debug & 2) && (t * n_kc * taps + blk) >= P.w_stages) {
+                        if (elect_one()) mbar_arrive(full);
+                        __syncwarp();
+                        src += P.w_stage_bytes;
+                        if (++stage == P.w_stages) { stage = 0; phase ^= 1u; }
+                        continue;
+                    }
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(full, (uint32_t)P.w_stage_bytes);
+                        bulk_load_1d(w_base + stage * (uint32_t)P.w_stage_bytes, src, (uint32_t)P.w_stage_bytes, full);
+                    }
+                    __syncwarp();
                     src += P.w_stage_bytes;
                     if (++stage == P.w_stages) { stage = 0; phase ^= 1u; }
                 }
@@ -216,7 +248,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
         }
     } else if (warp == 2) {
         // ===== MMA issuer =====
-        if (lane == 0) {
+        {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t H16 = (uint32_t)P.halo * 16u;          // one chunk row of the halo tile
             const uint32_t a_lbo = H16, a_sbo = 4u * H16;
@@ -250,21 +282,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                                 const uint64_t ah0 = cv_desc(a_hi, a_lbo_f, a_hi_word);
                                 const uint64_t al0 = cv_desc(a_hi + (uint32_t)P.a_unit_bytes, a_lbo_f, a_hi_word);
                                 const uint64_t astep = (uint64_t)((2u * a_lbo) >> 4);
-#pragma unroll
-                                for (int ks = 0; ks < 2; ++ks) {
-                                    umma_bf16(d, ah0 + ks * astep, wh0 + ks * wstep, idesc, (kc | tap | ks) != 0);
-                                    umma_bf16(d, al0 + ks * astep, wh0 + ks * wstep, idesc, 1);
-                                    umma_bf16(d, ah0 + ks * astep, wl0 + ks * wstep, idesc, 1);
+                                const uint32_t first = (uint32_t)((kc | tap) != 0);
+                                if (elect_one()) {
+                                    umma_bf16(d, ah0, wh0, idesc, first);
+                                    umma_bf16(d, al0, wh0, idesc, 1);
+                                    umma_bf16(d, ah0, wl0, idesc, 1);
+                                    umma_bf16(d, ah0 + astep, wh0 + wstep, idesc, 1);
+                                    umma_bf16(d, al0 + astep, wh0 + wstep, idesc, 1);
+                                    umma_bf16(d, ah0 + astep, wl0 + wstep, idesc, 1);
                                 }
+                                __syncwarp();
                             }
                         }
-                        if (!P.w_resident) umma_commit(cv_smem_u32(&bars.w_empty[ws]));   // weight block free once these MMAs retire
+                        if (!P.w_resident) {
+                            if (elect_one()) umma_commit(cv_smem_u32(&bars.w_empty[ws]));   // weight block free once these MMAs retire
+                            __syncwarp();
+                        }
                         if (++ws == P.w_stages) { ws = 0; wph ^= 1u; }
                     }
-                    umma_commit(cv_smem_u32(&bars.a_empty[as]));          // halo chunk free
+                    if (elect_one()) umma_commit(cv_smem_u32(&bars.a_empty[as]));          // halo chunk free
+                    __syncwarp();
                     if (++as == P.a_stages) { as = 0; aph ^= 1u; }
                 }
-                umma_commit(cv_smem_u32(&bars.acc_full[set]));            // accumulators of this tile complete
+                if (elect_one()) umma_commit(cv_smem_u32(&bars.acc_full[set]));            // accumulators of this tile complete
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -311,7 +352,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                             for (int j = 16; j < 32; ++j) v[j] = 0u;
                         }
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                        if (valid) {
+                        if (valid && !(P.debug & 4)) {
 #pragma unroll
                             for (int h = 0; h < 4; ++h) {
                                 const int c8 = ch * 4 + h;
@@ -504,6 +545,8 @@ extern "C" int pdm_conv_tc_forward(int b, int y, int x, int cin, int cout, int k
     if (w_fit < 2) return fail(PDM_ERR_UNSUPPORTED, "conv_tc_forward: operands do not fit in shared memory");
     P.w_resident = (w_fit >= n_blocks && n_blocks <= kCvMaxWStages) ? 1 : 0;
     P.w_stages = P.w_resident ? n_blocks : (w_fit < 8 ? w_fit : 8);
+    static const int dbg = [] { const char *e = getenv("PDM_CONV_DEBUG"); return e ? atoi(e) : 0; }();
+    P.debug = dbg;
 
     CUtensorMap tmap;
     const cuuint64_t gdim[5] = {(cuuint64_t)x * 8, (cuuint64_t)(cin / 8), (cuuint64_t)y, (cuuint64_t)b, 2};

@@ -88,8 +88,11 @@ def test_reference_class_agnostic_nms_on_our_extension(trees):
     sel_o, sc_o = ours.model_nms_utils.class_agnostic_nms(scores, boxes, cfg, score_thresh=0.2)
     sel_r, sc_r = ref.model_nms_utils.class_agnostic_nms(scores, boxes, cfg, score_thresh=0.2)
     assert torch.equal(sel_o, sel_r) and torch.equal(sc_o, sc_r) and len(sel_o) > 10
+    # IoU values: the overlap construction is ill-conditioned for nearly coincident boxes (tests/test_nms_gpu.py
+    # test_iou_vs_oracle_and_reference), so values are compared tightly but not bit for bit; keep lists above are exact
     iou_o = ours.iou3d_nms_utils.boxes_iou3d_gpu(boxes[:300], boxes[300:500])
     iou_r = ref.iou3d_nms_utils.boxes_iou3d_gpu(boxes[:300], boxes[300:500])
-    assert torch.equal(iou_o, iou_r)
-    assert torch.equal(ours.iou3d_nms_utils.boxes_iou_bev(boxes[:200], boxes[100:300]),
-                       ref.iou3d_nms_utils.boxes_iou_bev(boxes[:200], boxes[100:300]))
+    assert float((iou_o - iou_r).abs().max()) < 1e-5
+    bev_o = ours.iou3d_nms_utils.boxes_iou_bev(boxes[:200], boxes[100:300])
+    bev_r = ref.iou3d_nms_utils.boxes_iou_bev(boxes[:200], boxes[100:300])
+    assert float((bev_o - bev_r).abs().max()) < 1e-5 and float(bev_o.diagonal(-100).min()) > 0.999
