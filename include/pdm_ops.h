@@ -48,7 +48,7 @@ void pdm_reset_launch_count(void);
 int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                 void *stream);
 
-/* Scheduling hint for pdm_farthest_point_sampling (process-wide; no reference counterpart -- the
+/* Scheduling hint for pdm_farthest_point_sampling (process-wide default; no reference counterpart -- the
  * reference has one kernel).  Results are bit-identical in every mode.
  *   AUTO:       on-chip kernel (one frame per SM, lowest latency) unless one call has more frames than SMs
  *   LATENCY:    always the on-chip kernel
@@ -58,6 +58,10 @@ int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz, float *te
 #define PDM_FPS_MODE_LATENCY 1
 #define PDM_FPS_MODE_THROUGHPUT 2
 int pdm_set_fps_mode(int mode);
+/* The same sampling with the scheduling mode given per call (no process-wide state: two pipelines or threads in
+ * one process can use different modes); pdm_set_fps_mode only sets the default of the plain entry above. */
+int pdm_farthest_point_sampling_ex(int b, int n, int m, const float *xyz, float *temp, int *idx, int mode,
+                                   void *stream);
 
 /* gather_points_wrapper (pointnet2_api.cpp:16, sampling.cpp:14-23, sampling_gpu.cu:15-51).
  * points (B,C,N), idx (B,M) -> out (B,C,M). */

@@ -4,8 +4,10 @@ The product path has no CPU fallback: if the shared library is missing or does n
 export a symbol, importing/using the ops raises.  (`python -m pdm_ssd_b200.build`
 or `__graft_entry__.build()` produces the library; it is built in-tree.)
 """
+import contextlib
 import ctypes
 import os
+import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_HERE, "libpdmops.so")
@@ -18,6 +20,7 @@ _f = ctypes.c_float
 SIGNATURES = {
     "pdm_set_fps_mode": [_i],
     "pdm_farthest_point_sampling": [_i, _i, _i, _vp, _vp, _vp, _vp],
+    "pdm_farthest_point_sampling_ex": [_i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "pdm_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pdm_gather_points_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pdm_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
@@ -85,8 +88,30 @@ FPS_MODE_AUTO, FPS_MODE_LATENCY, FPS_MODE_THROUGHPUT = 0, 1, 2
 
 
 def set_fps_mode(mode):
-    """Scheduling hint for farthest point sampling (include/pdm_ops.h); results do not depend on it."""
+    """Process-wide default scheduling hint for farthest point sampling (include/pdm_ops.h); results do not
+    depend on it.  Prefer `fps_mode(...)`, which is per thread and passed per call."""
     check(load().pdm_set_fps_mode(int(mode)), "set_fps_mode")
+
+
+_tls = threading.local()
+
+
+def current_fps_mode():
+    """Mode the calling thread asked for with `fps_mode(...)`, or None (= the process-wide default)."""
+    return getattr(_tls, "fps_mode", None)
+
+
+@contextlib.contextmanager
+def fps_mode(mode):
+    """`with _lib.fps_mode(_lib.FPS_MODE_THROUGHPUT): ...` -- every farthest-point-sampling call this thread
+    makes inside the block (also while a CUDA graph is being captured) carries the mode as an argument
+    (pdm_farthest_point_sampling_ex): no process-wide state, other threads / pipelines are unaffected."""
+    prev = getattr(_tls, "fps_mode", None)
+    _tls.fps_mode = int(mode)
+    try:
+        yield
+    finally:
+        _tls.fps_mode = prev
 
 
 def launch_count():

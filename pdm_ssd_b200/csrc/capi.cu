@@ -52,26 +52,52 @@ void prefer_max_smem(const void *func) {
         (void)cudaGetLastError();   // a hint only: never fail a launch over it
 }
 
+// Scratch ownership.
+//   * Eager calls on a stream share one buffer per (device, stream): work on a stream is serialised.  When it has
+//     to grow, the old buffer is released (cudaFree synchronises the device, so nothing can still be using it).
+//   * A call made while its stream is being CAPTURED gets a buffer that belongs to that capture alone (keyed by
+//     the capture id): the first such call adopts the stream's eager buffer -- sized by the warm-up run every
+//     capture needs anyway, allocation is not possible during capture -- and the stream's eager slot is emptied,
+//     so later eager calls, and later captures on the same stream, get a different buffer.  Two graphs therefore
+//     never share scratch, whatever streams they are replayed on (a graph does not run concurrently with itself),
+//     and eager work on the capture stream cannot collide with a replay either.  The calls inside ONE graph are
+//     ordered by the captured dependencies of that stream and share the graph's buffer.
+//   Buffers adopted by a capture stay allocated for the life of the process (the library cannot see a graph die);
+//   that is bounded by the number of captures, not by the number of calls.
 void *stream_scratch(cudaStream_t st, size_t bytes) {
     struct Buf { void *ptr = nullptr; size_t size = 0; };
     static std::mutex mu;
-    static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+    static std::map<std::pair<int, cudaStream_t>, Buf> eager;
+    static std::map<std::pair<int, unsigned long long>, Buf> captured;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { fail(PDM_ERR_INVALID_ARG, "stream_scratch: cudaGetDevice failed"); return nullptr; }
-    std::lock_guard<std::mutex> lock(mu);
-    Buf &b = bufs[{dev, st}];
-    if (bytes <= b.size) return b.ptr;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(st, &cap);
+    unsigned long long cap_id = 0;
+    if (cudaStreamGetCaptureInfo(st, &cap, &cap_id) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    std::lock_guard<std::mutex> lock(mu);
     if (cap != cudaStreamCaptureStatusNone) {
-        fail(PDM_ERR_UNSUPPORTED, "scratch would grow to %zu B during stream capture: run the call once before capturing", bytes);
+        Buf &g = captured[{dev, cap_id}];
+        if (!g.ptr) {                       // first scratch user of this capture: adopt the stream's eager buffer
+            Buf &e = eager[{dev, st}];
+            g = e;
+            e = Buf();
+        }
+        if (bytes <= g.size) return g.ptr;
+        fail(PDM_ERR_UNSUPPORTED, "scratch of %zu B needed during stream capture but only %zu B were prepared: run the same "
+             "calls once on this stream before capturing", bytes, g.size);
         return nullptr;
     }
+    Buf &b = eager[{dev, st}];
+    if (bytes <= b.size) return b.ptr;
     const size_t want = bytes + bytes / 4;   // head-room so that slightly larger calls do not reallocate
+    if (b.ptr) {
+        if (cudaFree(b.ptr) != cudaSuccess) (void)cudaGetLastError();   // implicit device synchronisation: no user left
+        b = Buf();
+    }
     void *p = nullptr;
     const cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) { fail((int)e, "stream_scratch: cudaMalloc(%zu): %s", want, cudaGetErrorString(e)); return nullptr; }
-    b.ptr = p;      // the outgrown buffer stays allocated: earlier work / captured graphs may still use it
+    b.ptr = p;
     b.size = want;
     return p;
 }

@@ -102,13 +102,11 @@ int ensure_dynamic_smem(const void *func, size_t bytes);
 // PDM_CARVEOUT=off disables it (A/B measurements).
 void prefer_max_smem(const void *func);
 
-// Persistent scratch, one buffer per (device, stream), grown on demand and never moved while in
-// use: work on one stream is serialised, so consecutive calls can share it, and a CUDA graph that
-// captured a call keeps a valid address (buffers that were outgrown are retired, not freed).
-// Stream-ordered cudaMallocAsync inside a captured step turned every graph launch into ~1 ms of
-// driver work once four processes drove four GPUs; a plain pointer costs nothing.
-// Returns nullptr and records an error if the buffer would have to grow during stream capture
-// (run the call once eagerly first).
+// Library scratch (ball-query grid, NMS masks, neck work lists, FPS throughput mode): one buffer per (device,
+// stream) for eager calls, one PRIVATE buffer per stream capture for calls recorded into a CUDA graph (see
+// capi.cu for the ownership rules).  Stream-ordered cudaMallocAsync inside a captured step turned every graph
+// launch into ~1 ms of driver work once four processes drove four GPUs; a plain pointer costs nothing.
+// Returns nullptr and records an error if a captured call needs more than the warm-up run prepared.
 void *stream_scratch(cudaStream_t st, size_t bytes);
 
 // reference host helper cuda_utils.h:10-14 (block size the reference FPS would use);

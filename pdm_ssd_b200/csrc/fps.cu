@@ -538,7 +538,7 @@ static int launch_cap(int nw, int kmax, int b, int n, int m, int p, const float 
 static std::atomic<int> g_fps_mode{PDM_FPS_MODE_AUTO};
 
 static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int *idx, int *stats,
-                        cudaStream_t st) {
+                        cudaStream_t st, int mode_arg = -1) {
     const int bs = ref_fps_block_size(n);
     int p = 0;
     while ((1 << p) < bs) ++p;
@@ -546,7 +546,8 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
     const bool generic = force && force[0] == 'g';
     // throughput variant (fps_l2.cu): asked for by the caller (pdm_set_fps_mode) or when one launch
     // alone has more frames than the GPU has SMs
-    const int mode = g_fps_mode.load(std::memory_order_relaxed);
+    // per call (pdm_farthest_point_sampling_ex) or the process-wide default (pdm_set_fps_mode)
+    const int mode = mode_arg >= 0 ? mode_arg : g_fps_mode.load(std::memory_order_relaxed);
     const bool want_l2 = force ? force[0] == 'l' : (mode == PDM_FPS_MODE_THROUGHPUT || (mode == PDM_FPS_MODE_AUTO && b > kNumSMs));
     static const int l2_min_n = [] { const char *e = getenv("PDM_FPS_L2_MIN_N"); return e ? atoi(e) : 0; }();
     if (!generic && want_l2 && n >= l2_min_n && fps_l2_supports(n)) return fps_l2_launch(b, n, m, p, xyz, temp, idx, stats, st);
@@ -608,13 +609,26 @@ extern "C" int pdm_set_fps_mode(int mode) {
     return PDM_OK;
 }
 
+static int fps_entry(int b, int n, int m, const float *xyz, float *temp, int *idx, int mode, void *stream);
+
 extern "C" int pdm_farthest_point_sampling(int b, int n, int m, const float *xyz, float *temp,
                                            int *idx, void *stream) {
+    return fps_entry(b, n, m, xyz, temp, idx, -1, stream);
+}
+
+extern "C" int pdm_farthest_point_sampling_ex(int b, int n, int m, const float *xyz, float *temp,
+                                              int *idx, int mode, void *stream) {
+    if (mode < PDM_FPS_MODE_AUTO || mode > PDM_FPS_MODE_THROUGHPUT)
+        return pdm::fail(PDM_ERR_INVALID_ARG, "farthest_point_sampling_ex: unknown mode %d", mode);
+    return fps_entry(b, n, m, xyz, temp, idx, mode, stream);
+}
+
+static int fps_entry(int b, int n, int m, const float *xyz, float *temp, int *idx, int mode, void *stream) {
     using namespace pdm;
     if (b < 0 || n < 0 || m < 0) return fail(PDM_ERR_INVALID_ARG, "farthest_point_sampling: negative size");
     if (b == 0 || m == 0) return PDM_OK;
     if (n == 0) return fail(PDM_ERR_INVALID_ARG, "farthest_point_sampling: n == 0 with m > 0");
     if (!xyz || !temp || !idx) return fail(PDM_ERR_INVALID_ARG, "farthest_point_sampling: null pointer");
     if ((long long)n * 3 > 0x7fffffffLL) return fail(PDM_ERR_UNSUPPORTED, "farthest_point_sampling: n too large");
-    return fps_dispatch(b, n, m, xyz, temp, idx, nullptr, (cudaStream_t)stream);
+    return fps_dispatch(b, n, m, xyz, temp, idx, nullptr, (cudaStream_t)stream, mode);
 }

@@ -43,9 +43,13 @@ def farthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_ten
     t = _chk(temp_tensor, "temp", _F32)
     i = _chk(idx_tensor, "idx", _I32)
     _need(points_tensor, "points", b * n * 3); _need(temp_tensor, "temp", b * n); _need(idx_tensor, "idx", b * m)
+    mode = _lib.current_fps_mode()          # per-thread scheduling hint (`with _lib.fps_mode(...)`), passed per call
     with torch.cuda.device(points_tensor.device):
-        _lib.check(lib.pdm_farthest_point_sampling(b, n, m, p, t, i, _stream(points_tensor)),
-                   "farthest_point_sampling")
+        if mode is None:
+            rc = lib.pdm_farthest_point_sampling(b, n, m, p, t, i, _stream(points_tensor))
+        else:
+            rc = lib.pdm_farthest_point_sampling_ex(b, n, m, p, t, i, mode, _stream(points_tensor))
+        _lib.check(rc, "farthest_point_sampling")
     return 1
 
 

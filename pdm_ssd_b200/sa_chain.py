@@ -150,13 +150,13 @@ class PipelinedSAChain:
     fill the other SMs; per-batch latency is unchanged.  `host=True` adds the pinned-host H2D /
     D2H copies of HostSAChain to every step (on the step's stream, overlapping other steps).
 
-    `capture(slot_args)` records each slot's step (all kernel launches, copies and the stream-ordered
-    scratch allocations) into a CUDA graph bound to that slot's static input buffers; `submit()`
+    `capture(slot_args)` records each slot's step (all kernel launches and copies; the library's scratch
+    buffer of the slot's stream becomes private to the graph, csrc/capi.cu) into a CUDA graph bound to that slot's static input buffers; `submit()`
     then replays graphs, which removes the ~0.8 ms of Python/launch overhead per step that otherwise
     bounds the pipeline once four or more batches are in flight.
 
     `fps_mode`: scheduling hint for farthest point sampling while the steps are captured / run
-    (`_lib.FPS_MODE_*`, include/pdm_ops.h).  With many batches in flight the THROUGHPUT kernel (several
+    (`_lib.FPS_MODE_*`, include/pdm_ops.h; passed per call, no process-wide state).  With many batches in flight the THROUGHPUT kernel (several
     frames per SM) gives more frames/s at a longer per-batch latency; results are bit-identical."""
 
     def __init__(self, batch, n_streams=4, n_points=16384, layers=KITTI_CHAIN, device="cuda:0", host=False, backend=None,
@@ -182,12 +182,10 @@ class PipelinedSAChain:
         self.slot_args, self.graphs = list(slot_args), []
         torch.cuda.synchronize(self.dev)
         if self.fps_mode is not None:
-            _lib.set_fps_mode(self.fps_mode)      # the captured graphs keep the kernels chosen now
-        try:
+            with _lib.fps_mode(self.fps_mode):    # per call, per thread: the captured graphs keep the kernels chosen now
+                self._capture_all(_lib)
+        else:
             self._capture_all(_lib)
-        finally:
-            if self.fps_mode is not None:
-                _lib.set_fps_mode(_lib.FPS_MODE_AUTO)
         torch.cuda.synchronize(self.dev)
 
     def _capture_all(self, _lib):
