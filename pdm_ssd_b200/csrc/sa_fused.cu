@@ -379,6 +379,12 @@ sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__r
 
 }  // namespace pdm
 
+namespace pdm {
+int sa_rows_try(int b, int n, int m, int c_feat, int nsample, int use_xyz, const float *xyz, const float *feats,
+                const float *new_xyz, const int *idx, int n_layers, const int *widths, const float *packed, float *out,
+                float *out_pm, cudaStream_t st);   // sa_rows.cu
+}
+
 // packed: for each layer l, Wt[k][wpad(l+1)] (k < width[l]; transposed, BN folded, zero padded
 // columns) followed by bias[wpad(l+1)]; offsets are derived here from `widths`.
 // packed_tc (optional): operands of the tensor-core kernel, see SATCParams.
@@ -415,6 +421,15 @@ extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample
     if (!xyz || !new_xyz || !idx || !packed || !out || (c_feat > 0 && !features))
         return fail(PDM_ERR_INVALID_ARG, "sa_fused_forward: null pointer");
     if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "sa_fused_forward: batch > 65535");
+    // narrow MLPs (first SA layer): thread-per-row kernel, everything in registers (sa_rows.cu); PDM_SA_ROWS=0 disables
+    {
+        static const bool rows_off = [] { const char *e = getenv("PDM_SA_ROWS"); return e && e[0] == '0'; }();
+        if (!rows_off) {
+            const int rc = sa_rows_try(b, n, m, c_feat, nsample, use_xyz, xyz, features, new_xyz, idx, n_layers, widths, packed, out,
+                                       nullptr, (cudaStream_t)stream);
+            if (rc >= 0 || rc < -1) return rc;
+        }
+    }
     // tensor-core path (tcgen05) whenever its operands were supplied and the scale fits;
     // PDM_SA_TC=0 forces the CUDA-core kernel
     {

@@ -127,6 +127,9 @@ def _randomise_bn(module, seed):
     (2048, 300, 5, 64, [5, 32], False),                 # one layer, no xyz channels
     (2048, 77, 0, 128, [0, 24, 24, 24, 40], True),      # xyz only, four layers, one centre per CTA
     (1024, 64, 3, 4, [3, 128], True),                   # tiny groups, widest layer
+    (4096, 1000, 1, 16, [1, 16, 32], True),             # thread-per-row kernel: two layers, two centres per warp, ragged tail
+    (2048, 333, 5, 32, [5, 32, 32, 64], True),          # thread-per-row kernel: 8 input channels, widest instantiation
+    (2048, 256, 4, 32, [4, 16, 32, 64], False),         # thread-per-row kernel without xyz channels
 ])
 def test_fused_sa_scale_matches_unfused_path(N, M_, C, S, mlp, use_xyz, monkeypatch):
     torch.manual_seed(N + S)
