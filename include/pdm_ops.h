@@ -137,6 +137,20 @@ int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample, int use_x
                          const int *widths, const float *packed, const float *packed_tc, float *out,
                          void *stream);
 
+/* pdm_sa_fused_forward with the optional operands of the faster kernels (all may be NULL):
+ *   features_pm  the same features point-major (B, N, c_feat): the gather reads a row's channels from one place
+ *   packed_tc3 / bias_tc3  operands of the persistent tcgen05 kernel (csrc/sa_tc.cu): per layer the BN-folded
+ *                weights W'[n][k] as three bf16 planes hi|mid|lo (hi + mid + lo = w to 2^-24), each plane
+ *                [kpad/8][npad][8] with kpad, npad = widths rounded up to 16, layers back to back; bias fp32 [n_layers][128]
+ *   out_pm       the result also written point-major (B, M, widths[n_layers]) -- what the next layer's gather and the
+ *                detector's `point_features` (pointnet2_backbone.py:91-92) read
+ * Kernel choice per scale: thread-per-row (narrow MLPs, csrc/sa_rows.cu), persistent tcgen05 (nsample 32, hidden widths
+ * <= 64, output <= 128), round 1's tcgen05 kernel, CUDA cores. */
+int pdm_sa_fused_forward_v2(int b, int n, int m, int c_feat, int nsample, int use_xyz, const float *xyz,
+                            const float *features, const float *features_pm, const float *new_xyz, const int *idx,
+                            int n_layers, const int *widths, const float *packed, const float *packed_tc,
+                            const void *packed_tc3, const float *bias_tc3, float *out, float *out_pm, void *stream);
+
 /* ---- PDM neck (SPEC_PDM.md) ---------------------------------------------------------- */
 
 /* Point dilation + SH/Gaussian feature filling + multi-centre fusion + height compression.

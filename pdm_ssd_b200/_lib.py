@@ -31,6 +31,7 @@ SIGNATURES = {
     "pdm_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pdm_query_and_group": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pdm_sa_fused_forward": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _vp, _vp, _vp, _vp],
+    "pdm_sa_fused_forward_v2": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "pdm_neck_forward": [_i, _i, _i, _vp, _vp, _vp, ctypes.POINTER(_f), ctypes.POINTER(_f),
                          ctypes.POINTER(_i), ctypes.POINTER(_i), _i, _f, _f, _vp, _vp, _vp, _vp],
     "pdm_boxes_iou_bev": [_i, _vp, _i, _vp, _vp, _vp],

@@ -19,6 +19,11 @@ import torch.nn as nn
 from . import pointnet2_modules
 
 
+# Device-side (asynchronous, no host sync) check that `points[:, 0]` really is 0..B-1 in equal blocks.  Off by default:
+# it adds two small kernels per forward; tests and debugging switch it on.
+CHECK_BATCH_INDEX = False
+
+
 class AttrDict(dict):
     """Minimal EasyDict stand-in (pcdet/config.py uses easydict): attribute access + .get, nested."""
 
@@ -42,6 +47,11 @@ def _split_points(points, batch_size):
         raise RuntimeError("points rows (%d) are not a multiple of batch_size (%d): frames must carry "
                            "the same number of points (data_processor.sample_points)" % (points.shape[0], batch_size))
     batch_idx = points[:, 0]
+    if CHECK_BATCH_INDEX:
+        # the reference checks per-frame counts with one .sum() per frame (pointnet2_backbone.py:72-76: batch_size + 2
+        # host syncs); here a device-side assertion: rows must be grouped by frame, `rows / batch_size` per frame
+        want = torch.arange(batch_size, device=points.device, dtype=points.dtype).repeat_interleave(points.shape[0] // batch_size)
+        torch._assert_async((batch_idx == want).all(), "points are not grouped by frame with equal counts")
     xyz = points[:, 1:4].contiguous().view(batch_size, -1, 3)
     feats = None
     if points.size(-1) > 4:
@@ -104,5 +114,9 @@ class PDMSSDBackbone(nn.Module):
         M = xyz.shape[1]
         bcol = torch.arange(B, device=xyz.device, dtype=torch.float32).repeat_interleave(M)[:, None]
         batch_dict['point_coords'] = torch.cat((bcol, xyz.reshape(-1, 3)), dim=1)
-        batch_dict['point_features'] = feats.permute(0, 2, 1).reshape(B * M, -1).contiguous()
+        pm = getattr(feats, '_pdm_point_major', None)          # (B, M, C) written by the fused SA kernel
+        if pm is not None and pm.shape == (B, M, feats.shape[1]):
+            batch_dict['point_features'] = pm.view(B * M, -1)
+        else:
+            batch_dict['point_features'] = feats.permute(0, 2, 1).reshape(B * M, -1).contiguous()
         return batch_dict

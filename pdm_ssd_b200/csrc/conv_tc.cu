@@ -34,7 +34,7 @@
 
 #include <mutex>
 
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pdm {
 
@@ -58,76 +58,6 @@ struct ConvTCParams {
     int debug;           // PDM_CONV_DEBUG (measurement only, results wrong): 1 halo loads only while the ring fills,
                          // 2 same for weight blocks, 4 no global stores in the epilogue
 };
-
-__device__ __forceinline__ uint32_t cv_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t done;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    return done;
-}
-__device__ __forceinline__ unsigned long long cv_globaltimer() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// Bounded wait: ~2 s of wall clock, then error word + trap.  `code` says which barrier gave up.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *err, int code) {
-    if (mbar_try_wait(bar, parity)) return;
-    const unsigned long long t0 = cv_globaltimer();
-    for (;;) {
-#pragma unroll 1
-        for (int it = 0; it < 256; ++it)
-            if (mbar_try_wait(bar, parity)) return;
-        if (cv_globaltimer() - t0 > 2000000000ull) {
-            if (err) atomicExch(err, code);
-            __threadfence_system();
-            __trap();
-        }
-    }
-}
-
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap *tm, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-                 :: "r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-// K-major, SWIZZLE_NONE shared-memory matrix descriptor (version 1 at bit 46): the high word (SBO, version) is
-// fixed per operand, the low word carries the start address and LBO
-__device__ __forceinline__ uint32_t cv_desc_hi(uint32_t sbo_bytes) { return ((sbo_bytes >> 4) & 0x3fffu) | (1u << 14); }
-__device__ __forceinline__ uint64_t cv_desc(uint32_t saddr, uint32_t lbo_field, uint32_t hi) {
-    return (uint64_t)(((saddr >> 4) & 0x3fffu) | lbo_field) | ((uint64_t)hi << 32);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-                 :: "r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// One lane of a converged warp.  The role loops below stay warp-uniform (every lane waits on the barriers and
-// computes the descriptors, which therefore live in uniform registers) and only the issuing instruction sits
-// under this predicate; a loop that is entered by `lane == 0` alone makes ptxas wrap every tcgen05.mma / TMA
-// instruction in an ELECT ... BRA.U.ANY uniformisation loop plus R2UR moves (measured: ~85 cycles per MMA).
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
-    return pred != 0;
-}
 
 struct __align__(8) ConvBarriers {
     uint64_t a_full[kCvMaxAStages], a_empty[kCvMaxAStages];

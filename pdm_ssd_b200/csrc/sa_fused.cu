@@ -310,7 +310,11 @@ sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__r
                 for (int it = 0; it < (1 << 20) && !done; ++it)
                     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                                  : "=r"(done) : "r"(smem_u32(&bar)), "r"(phase) : "memory");
-                if (!done && lane == 0 && err) atomicExch(err, 1);
+                if (!done) {              // never continue past an unsatisfied barrier: the launch fails loudly
+                    if (lane == 0 && err) atomicExch(err, 1);
+                    __threadfence_system();
+                    __trap();
+                }
             }
             phase ^= 1u;
             asm volatile("tcgen05.fence::before_thread_sync;");
@@ -380,6 +384,9 @@ sa_fused_tc_kernel(SATCParams P, const float *__restrict__ xyz, const float *__r
 }  // namespace pdm
 
 namespace pdm {
+int sa_tc3_try(int b, int n, int m, int c_feat, int nsample, int use_xyz, const float *xyz, const float *feats,
+               const float *feats_pm, const float *new_xyz, const int *idx, int n_layers, const int *widths,
+               const void *wpacked, const float *bias, float *out, float *out_pm, cudaStream_t st);   // sa_tc.cu
 int sa_rows_try(int b, int n, int m, int c_feat, int nsample, int use_xyz, const float *xyz, const float *feats,
                 const float *new_xyz, const int *idx, int n_layers, const int *widths, const float *packed, float *out,
                 float *out_pm, cudaStream_t st);   // sa_rows.cu
@@ -388,10 +395,46 @@ int sa_rows_try(int b, int n, int m, int c_feat, int nsample, int use_xyz, const
 // packed: for each layer l, Wt[k][wpad(l+1)] (k < width[l]; transposed, BN folded, zero padded
 // columns) followed by bias[wpad(l+1)]; offsets are derived here from `widths`.
 // packed_tc (optional): operands of the tensor-core kernel, see SATCParams.
+extern "C" int pdm_sa_fused_forward_v2(int b, int n, int m, int c_feat, int nsample, int use_xyz,
+                                       const float *xyz, const float *features, const float *features_pm,
+                                       const float *new_xyz, const int *idx, int n_layers, const int *widths,
+                                       const float *packed, const float *packed_tc, const void *packed_tc3,
+                                       const float *bias_tc3, float *out, float *out_pm, void *stream);
+
 extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample, int use_xyz,
                                     const float *xyz, const float *features, const float *new_xyz,
                                     const int *idx, int n_layers, const int *widths,
                                     const float *packed, const float *packed_tc, float *out, void *stream) {
+    return pdm_sa_fused_forward_v2(b, n, m, c_feat, nsample, use_xyz, xyz, features, nullptr, new_xyz, idx, n_layers, widths,
+                                   packed, packed_tc, nullptr, nullptr, out, nullptr, stream);
+}
+
+namespace pdm {
+// (B, C, M) -> (B, M, C) for the kernels that do not write the point-major copy themselves
+__global__ void __launch_bounds__(256)
+to_point_major_kernel(int bm_total, int m, int c, const float *__restrict__ in, float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)bm_total * c) return;
+    const int ch = (int)(i % c);
+    const long long cm = i / c;
+    const int bi = (int)(cm / m), mi = (int)(cm - (long long)bi * m);
+    out[i] = __ldg(in + ((size_t)bi * c + ch) * m + mi);
+}
+static int finish_point_major(int b, int m, int c, const float *out, float *out_pm, cudaStream_t st) {
+    if (!out_pm) return PDM_OK;
+    const long long total = (long long)b * m * c;
+    to_point_major_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(b * m, m, c, out, out_pm);
+    count_launch();
+    PDM_CHECK_LAUNCH("sa_fused_forward(point-major copy)");
+    return PDM_OK;
+}
+}  // namespace pdm
+
+extern "C" int pdm_sa_fused_forward_v2(int b, int n, int m, int c_feat, int nsample, int use_xyz,
+                                       const float *xyz, const float *features, const float *features_pm,
+                                       const float *new_xyz, const int *idx, int n_layers, const int *widths,
+                                       const float *packed, const float *packed_tc, const void *packed_tc3,
+                                       const float *bias_tc3, float *out, float *out_pm, void *stream) {
     using namespace pdm;
     if (b < 0 || n < 0 || m < 0 || c_feat < 0 || nsample <= 0)
         return fail(PDM_ERR_INVALID_ARG, "sa_fused_forward: bad size");
@@ -423,10 +466,22 @@ extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample
     if (b > 65535) return fail(PDM_ERR_UNSUPPORTED, "sa_fused_forward: batch > 65535");
     // narrow MLPs (first SA layer): thread-per-row kernel, everything in registers (sa_rows.cu); PDM_SA_ROWS=0 disables
     {
-        static const bool rows_off = [] { const char *e = getenv("PDM_SA_ROWS"); return e && e[0] == '0'; }();
+        const char *er = getenv("PDM_SA_ROWS");
+        const bool rows_off = er && er[0] == '0';
         if (!rows_off) {
             const int rc = sa_rows_try(b, n, m, c_feat, nsample, use_xyz, xyz, features, new_xyz, idx, n_layers, widths, packed, out,
-                                       nullptr, (cudaStream_t)stream);
+                                       out_pm, (cudaStream_t)stream);
+            if (rc >= 0 || rc < -1) return rc;
+        }
+    }
+    // genuine GEMMs (second SA layer): persistent warp-specialised tcgen05 kernel (sa_tc.cu); PDM_SA_TC3=0 disables
+    {
+        const char *e3 = getenv("PDM_SA_TC3");      // read per call: tools toggle it within a process
+        const bool tc3_off = e3 && e3[0] == '0';
+        const char *env = getenv("PDM_SA_TC");
+        if (!tc3_off && packed_tc3 && bias_tc3 && !(env && env[0] == '0')) {
+            const int rc = sa_tc3_try(b, n, m, c_feat, nsample, use_xyz, xyz, features, features_pm, new_xyz, idx, n_layers, widths,
+                                      packed_tc3, bias_tc3, out, out_pm, (cudaStream_t)stream);
             if (rc >= 0 || rc < -1) return rc;
         }
     }
@@ -468,7 +523,7 @@ extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample
             sa_fused_tc_kernel<<<grid, kTCThreads, smem_tc, (cudaStream_t)stream>>>(T, xyz, features, new_xyz, idx, packed_tc, out, nullptr);
             count_launch();
             PDM_CHECK_LAUNCH("sa_fused_forward(tcgen05)");
-            return PDM_OK;
+            return finish_point_major(b, m, widths[n_layers], out, out_pm, (cudaStream_t)stream);
         }
     }
     const size_t smem = sizeof(float) * ((size_t)2 * P.act_floats + P.w_floats + kSAMaxC);
@@ -478,5 +533,5 @@ extern "C" int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample
     sa_fused_kernel<<<grid, kSAThreads, smem, (cudaStream_t)stream>>>(P, xyz, features, new_xyz, idx, packed, out);
     count_launch();
     PDM_CHECK_LAUNCH("sa_fused_forward");
-    return PDM_OK;
+    return finish_point_major(b, m, widths[n_layers], out, out_pm, (cudaStream_t)stream);
 }

@@ -72,6 +72,32 @@ def _pack_folded_tc(folded):
     return torch.cat([bias.reshape(-1)] + chunks).contiguous()
 
 
+def _pack_folded_tc3(folded):
+    """Operands of the persistent tcgen05 kernel (csrc/sa_tc.cu): per layer the folded weights W'[n][k] as three
+    bf16 planes hi|mid|lo (hi + mid + lo = w to 2^-24), each plane [kpad/8][npad][8] with kpad, npad = widths rounded
+    up to 16 -- the K-major no-swizzle core-matrix layout, so a layer is one straight bulk copy into shared memory;
+    bias fp32 (L, 128).  Returns (planes as a bf16 tensor, bias) or None when the stack does not fit the kernel."""
+    if len(folded) < 2 or len(folded) > 3:
+        return None
+    bias = folded[0][0].new_zeros((len(folded), 128))
+    chunks = []
+    for l, (w, b) in enumerate(folded):           # w (N, K)
+        n_out, k_in = w.shape
+        if n_out > 128 or k_in > 96:
+            return None
+        kpad, npad = (k_in + 15) // 16 * 16, (n_out + 15) // 16 * 16
+        wp = w.new_zeros((npad, kpad))
+        wp[:n_out, :k_in] = w
+        bias[l, :n_out] = b
+        hi = wp.to(torch.bfloat16)
+        r1 = wp - hi.float()
+        mid = r1.to(torch.bfloat16)
+        lo = (r1 - mid.float()).to(torch.bfloat16)
+        planes = torch.stack([hi, mid, lo]).reshape(3, npad, kpad // 8, 8).permute(0, 2, 1, 3)     # plane, k8, n, 8
+        chunks.append(planes.reshape(-1))
+    return torch.cat(chunks).contiguous(), bias.contiguous()
+
+
 def _shared_mlp(widths: List[int]) -> nn.Sequential:
     """1x1 Conv2d(bias=False) + BatchNorm2d + ReLU per hop (pointnet2_modules.py:90-97,132-139)."""
     layers = []
@@ -113,7 +139,7 @@ class _PointnetSAModuleBase(nn.Module):
                 continue
             grouped = grouper(xyz, new_xyz, features)          # (B, C_in, npoint, nsample)
             pooled.append(self._pool(mlp(grouped)).squeeze(-1))  # (B, C_out, npoint)
-        return new_xyz, torch.cat(pooled, dim=1)
+        return new_xyz, (pooled[0] if len(pooled) == 1 else torch.cat(pooled, dim=1))
 
     def _fused_scale(self, si, grouper, mlp, xyz, new_xyz, features):
         """(B, C_out, npoint) through csrc/sa_fused.cu, or None when the fast path does not apply."""
@@ -126,7 +152,9 @@ class _PointnetSAModuleBase(nn.Module):
         S = grouper.nsample
         if S < 4 or S > 128 or (S & (S - 1)) != 0 or (features is None and not grouper.use_xyz):
             return None
-        version = sum(p._version for p in mlp.parameters()) + sum(b._version for b in mlp.buffers())
+        # cache key: storage address + in-place version of every tensor of the stack (a replaced Parameter changes the
+        # address, an in-place update the version)
+        version = tuple((t.data_ptr(), t._version) for t in list(mlp.parameters()) + list(mlp.buffers()))
         cache = self.__dict__.setdefault('_fused_cache', {})
         hit = cache.get(si)
         if hit is None or hit[0] != version or hit[1].device != xyz.device:
@@ -136,9 +164,12 @@ class _PointnetSAModuleBase(nn.Module):
             else:
                 fl = [(w.detach().float(), b.detach().float()) for w, b in folded]
                 packed, widths = _pack_folded(fl)
-                cache[si] = (version, packed.to(xyz.device), widths, _pack_folded_tc(fl).to(xyz.device))
+                tc3 = _pack_folded_tc3(fl)
+                cache[si] = (version, packed.to(xyz.device), widths, _pack_folded_tc(fl).to(xyz.device),
+                             tc3[0].to(xyz.device) if tc3 is not None else None, tc3[1].to(xyz.device) if tc3 is not None else None)
             hit = cache[si]
         packed, widths, packed_tc = hit[1], hit[2], (hit[3] if len(hit) > 3 else None)
+        packed_tc3, bias_tc3 = (hit[4], hit[5]) if len(hit) > 5 else (None, None)
         if widths is None:
             return None
         B, N, _ = xyz.shape
@@ -146,19 +177,31 @@ class _PointnetSAModuleBase(nn.Module):
         c_feat = 0 if features is None else features.shape[1]
         if widths[0] != (3 if grouper.use_xyz else 0) + c_feat:
             return None
+        if features is not None and (features.dtype != torch.float32 or not features.is_cuda):
+            return None                                   # fp16 / fp64 / CPU features: the reference-shaped path handles them
         idx = pointnet2_utils.ball_query(grouper.radius, S, xyz, new_xyz)
         out = torch.empty((B, widths[-1], M), dtype=torch.float32, device=xyz.device)
+        out_pm = torch.empty((B, M, widths[-1]), dtype=torch.float32, device=xyz.device)
         feats = features.contiguous() if features is not None else None
+        # the same features point-major (B, N, C), when the producing SA layer left them (see below)
+        feats_pm = getattr(features, '_pdm_point_major', None) if features is not None else None
+        if feats_pm is not None and (feats_pm.shape != (B, N, c_feat) or not feats_pm.is_contiguous()):
+            feats_pm = None
         import ctypes
         warr = (ctypes.c_int * len(widths))(*widths)
         with torch.cuda.device(xyz.device):
-            rc = _lib.load().pdm_sa_fused_forward(
+            rc = _lib.load().pdm_sa_fused_forward_v2(
                 B, N, M, c_feat, S, 1 if grouper.use_xyz else 0, xyz.data_ptr(),
-                feats.data_ptr() if feats is not None else None, new_xyz.data_ptr(), idx.data_ptr(),
-                len(widths) - 1, warr, packed.data_ptr(),
-                packed_tc.data_ptr() if packed_tc is not None else None, out.data_ptr(),
+                feats.data_ptr() if feats is not None else None, feats_pm.data_ptr() if feats_pm is not None else None,
+                new_xyz.data_ptr(), idx.data_ptr(), len(widths) - 1, warr, packed.data_ptr(),
+                packed_tc.data_ptr() if packed_tc is not None else None,
+                packed_tc3.data_ptr() if packed_tc3 is not None else None,
+                bias_tc3.data_ptr() if bias_tc3 is not None else None, out.data_ptr(), out_pm.data_ptr(),
                 torch.cuda.current_stream(xyz.device).cuda_stream)
         _lib.check(rc, "pdm_sa_fused_forward")
+        # the kernels write the result twice: (B, C, M) for the API and (B, M, C) for whoever gathers rows next
+        # (the next SA layer, the backbone's `point_features`); the copy rides along as an attribute
+        out._pdm_point_major = out_pm
         return out
 
 
