@@ -105,6 +105,17 @@ int pdm_three_interpolate(int b, int c, int m, int n, const float *points, const
 int pdm_three_interpolate_grad(int b, int c, int n, int m, const float *grad_out, const int *idx,
                                const float *weight, float *grad_points, void *stream);
 
+/* Deterministic forms of the three gradient kernels above (same arguments, same "+=" contract).  The reference
+ * accumulates with atomicAdd (sampling_gpu.cu:53-70, group_points_gpu.cu:14-31, interpolate_gpu.cu:127-149), so the
+ * fp32 summation order changes from run to run; here every target sums its contributions in ascending source position
+ * (stable sort by target, then a serial in-order sum per target): bit-identical results on every run. */
+int pdm_gather_points_grad_det(int b, int c, int n, int npoints, const float *grad_out, const int *idx,
+                               float *grad_points, void *stream);
+int pdm_group_points_grad_det(int b, int c, int n, int npoints, int nsample, const float *grad_out,
+                              const int *idx, float *grad_points, void *stream);
+int pdm_three_interpolate_grad_det(int b, int c, int n, int m, const float *grad_out, const int *idx,
+                                   const float *weight, float *grad_points, void *stream);
+
 /* QueryAndGroup.forward after the ball query in one pass (pointnet2_utils.py:250-257: xyz^T copy,
  * group xyz, subtract centres, group features, cat).  xyz (B,N,3), new_xyz (B,npoints,3),
  * features (B,C,N) or NULL when c == 0, idx (B,npoints,nsample) ->
@@ -257,6 +268,21 @@ int pdm_point_head_forward(int p, int batch, int c_point, int c_bev, int y, int 
                            const float *b2_cls, const float *w2_box, const float *b2_box, const float *mean_size,
                            float *scores, float *boxes, float *best_score, int *best_label, float *cls_raw,
                            float *box_raw, void *stream);
+
+/* ---- input staging (csrc/sample_points.cu) ----------------------------------------------------------- */
+
+/* DataProcessor.sample_points (pcdet/datasets/processor/data_processor.py:182-212) for every frame of a batch, plus the
+ * `points` part of DatasetTemplate.collate_batch (pcdet/datasets/dataset.py:237-244), on the device.
+ *   points (total_points, c) fp32: the raw frames back to back, columns x, y, z, features...; counts (b) int32 DEVICE
+ *   array with the rows of each frame (their sum must equal total_points)
+ *   -> out (b * num_points, 1 + c) fp32 = [batch index, x, y, z, features...]: per frame exactly num_points rows chosen
+ *      and shuffled as the reference does (all far points kept, near points subsampled without replacement; short frames
+ *      padded with a random choice), the randomness defined by a counter-based hash of (seed, frame, index) -- see the
+ *      file header; oracle/sample_points_oracle.py is the numpy restatement.  choice (optional, b * num_points int32):
+ *      row of the source frame each output row was copied from (-1 for an empty frame).
+ * No host synchronisation; safe to capture in a CUDA graph after one eager call. */
+int pdm_sample_points(int b, int total_points, int c, int num_points, unsigned seed, const float *points,
+                      const int *counts, float *out, int *choice, void *stream);
 
 #ifdef __cplusplus
 }

@@ -29,6 +29,9 @@ SIGNATURES = {
     "pdm_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pdm_three_interpolate": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pdm_three_interpolate_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pdm_gather_points_grad_det": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pdm_group_points_grad_det": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
+    "pdm_three_interpolate_grad_det": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pdm_query_and_group": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
     "pdm_sa_fused_forward": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _vp, _vp, _vp, _vp],
     "pdm_sa_fused_forward_v2": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, ctypes.POINTER(_i), _vp, _vp, _vp, _vp, _vp, _vp, _vp],
@@ -44,6 +47,7 @@ SIGNATURES = {
     "pdm_linear_rows": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],
     "pdm_point_head_forward": [_i, _i, _i, _i, _i, _i, _i, _i, _i, ctypes.POINTER(_f), ctypes.POINTER(_f),
                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pdm_sample_points": [_i, _i, _i, _i, ctypes.c_uint, _vp, _vp, _vp, _vp, _vp],
     "pdm_act_split_bytes": [_i, _i, _i, _i, ctypes.POINTER(ctypes.c_longlong)],
     "pdm_act_split_from_nchw": [_i, _i, _i, _i, _vp, _vp, _vp],
     "pdm_act_split_to_nchw": [_i, _i, _i, _i, _vp, _vp, _vp],

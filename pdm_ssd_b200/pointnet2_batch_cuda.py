@@ -37,6 +37,12 @@ def _stream(ref):
     return torch.cuda.current_stream(ref.device).cuda_stream
 
 
+def _deterministic():
+    """The three gradient entries switch to the in-order (sorted, atomics-free) kernels of csrc/det_backward.cu when the
+    user asked torch for deterministic algorithms; the default matches the reference (atomicAdd, order unspecified)."""
+    return torch.are_deterministic_algorithms_enabled()
+
+
 def farthest_point_sampling_wrapper(b, n, m, points_tensor, temp_tensor, idx_tensor):
     lib = _lib.load()
     p = _chk(points_tensor, "points", _F32)
@@ -70,9 +76,9 @@ def gather_points_grad_wrapper(b, c, n, npoints, grad_out_tensor, idx_tensor, gr
     i = _chk(idx_tensor, "idx", _I32)
     o = _chk(grad_points_tensor, "grad_points", _F32)
     _need(grad_out_tensor, "grad_out", b * c * npoints); _need(idx_tensor, "idx", b * npoints); _need(grad_points_tensor, "grad_points", b * c * n)
+    fn = lib.pdm_gather_points_grad_det if _deterministic() else lib.pdm_gather_points_grad
     with torch.cuda.device(grad_out_tensor.device):
-        _lib.check(lib.pdm_gather_points_grad(b, c, n, npoints, g, i, o, _stream(grad_out_tensor)),
-                   "gather_points_grad")
+        _lib.check(fn(b, c, n, npoints, g, i, o, _stream(grad_out_tensor)), "gather_points_grad")
     return 1
 
 
@@ -106,9 +112,9 @@ def group_points_grad_wrapper(b, c, n, npoints, nsample, grad_out_tensor, idx_te
     o = _chk(grad_points_tensor, "grad_points", _F32)
     _need(grad_out_tensor, "grad_out", b * c * npoints * nsample); _need(idx_tensor, "idx", b * npoints * nsample)
     _need(grad_points_tensor, "grad_points", b * c * n)
+    fn = lib.pdm_group_points_grad_det if _deterministic() else lib.pdm_group_points_grad
     with torch.cuda.device(grad_out_tensor.device):
-        _lib.check(lib.pdm_group_points_grad(b, c, n, npoints, nsample, g, i, o, _stream(grad_out_tensor)),
-                   "group_points_grad")
+        _lib.check(fn(b, c, n, npoints, nsample, g, i, o, _stream(grad_out_tensor)), "group_points_grad")
     return 1
 
 
@@ -144,6 +150,6 @@ def three_interpolate_grad_wrapper(b, c, n, m, grad_out_tensor, idx_tensor, weig
     o = _chk(grad_points_tensor, "grad_points", _F32)
     _need(grad_out_tensor, "grad_out", b * c * n); _need(idx_tensor, "idx", b * n * 3)
     _need(weight_tensor, "weight", b * n * 3); _need(grad_points_tensor, "grad_points", b * c * m)
+    fn = lib.pdm_three_interpolate_grad_det if _deterministic() else lib.pdm_three_interpolate_grad
     with torch.cuda.device(grad_out_tensor.device):
-        _lib.check(lib.pdm_three_interpolate_grad(b, c, n, m, g, i, w, o, _stream(grad_out_tensor)),
-                   "three_interpolate_grad")
+        _lib.check(fn(b, c, n, m, g, i, w, o, _stream(grad_out_tensor)), "three_interpolate_grad")

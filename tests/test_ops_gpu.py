@@ -473,3 +473,55 @@ def test_query_and_group_fused_is_bit_identical(C, use_xyz, ref_ext):
     if ref_ext is not None:
         with pu.use_backend(ref_ext), torch.no_grad():
             assert torch.equal(pu.QueryAndGroup(1.2, 16, use_xyz=use_xyz)(fr, new_xyz, feats), fused)
+
+
+# ---- deterministic backward (csrc/det_backward.cu) -----------------------------------------------
+@pytest.fixture
+def deterministic():
+    prev = torch.are_deterministic_algorithms_enabled()
+    torch.use_deterministic_algorithms(True, warn_only=True)
+    yield
+    torch.use_deterministic_algorithms(prev)
+
+
+def test_deterministic_grads_match_oracle_and_repeat_bit_for_bit(deterministic):
+    """With torch.use_deterministic_algorithms(True) the gather / group / three_interpolate gradients are summed in
+    ascending source order: equal to the CPU oracle's serial sums to fp32 rounding, and bit-identical across runs even
+    with heavy collisions (every index hit ~100 times), where atomicAdd results wobble in the last bits."""
+    import oracle
+    from pdm_ssd_b200 import pointnet2_batch_cuda as be
+    rng = np.random.default_rng(11)
+    B, C, N, M, S = 3, 13, 257, 400, 32
+    idx = rng.integers(0, 40, (B, M, S)).astype(np.int32)            # 40 hot targets: long segments
+    go = rng.standard_normal((B, C, M, S)).astype(np.float32)
+    outs = []
+    for _ in range(3):
+        gp = torch.zeros((B, C, N), dtype=torch.float32, device=DEV)
+        be.group_points_grad_wrapper(B, C, N, M, S, torch.from_numpy(go).to(DEV), torch.from_numpy(idx).to(DEV), gp)
+        outs.append(gp.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+    np.testing.assert_allclose(outs[0], oracle.group_points_grad(go, idx, N), rtol=2e-5, atol=2e-5)
+    # gather
+    gi = rng.integers(0, 9, (B, M)).astype(np.int32)
+    gg = rng.standard_normal((B, C, M)).astype(np.float32)
+    a = torch.zeros((B, C, N), device=DEV)
+    b2 = torch.zeros((B, C, N), device=DEV)
+    be.gather_points_grad_wrapper(B, C, N, M, torch.from_numpy(gg).to(DEV), torch.from_numpy(gi).to(DEV), a)
+    be.gather_points_grad_wrapper(B, C, N, M, torch.from_numpy(gg).to(DEV), torch.from_numpy(gi).to(DEV), b2)
+    assert torch.equal(a, b2)
+    np.testing.assert_allclose(a.cpu().numpy(), oracle.gather_points_grad(gg, gi, N), rtol=2e-5, atol=2e-5)
+    # three_interpolate: (B, C, n) gradients to m known points through (idx, weight)
+    n, m = 500, 37
+    ti = rng.integers(0, m, (B, n, 3)).astype(np.int32)
+    tw = rng.uniform(0, 1, (B, n, 3)).astype(np.float32)
+    tg = rng.standard_normal((B, C, n)).astype(np.float32)
+    r = []
+    for _ in range(2):
+        gp = torch.zeros((B, C, m), device=DEV)
+        be.three_interpolate_grad_wrapper(B, C, n, m, torch.from_numpy(tg).to(DEV), torch.from_numpy(ti).to(DEV), torch.from_numpy(tw).to(DEV), gp)
+        r.append(gp.cpu().numpy())
+    assert np.array_equal(r[0], r[1])
+    np.testing.assert_allclose(r[0], oracle.three_interpolate_grad(tg, ti, tw, m), rtol=2e-5, atol=2e-5)
+    # "+=" contract: a second call accumulates on top of the first
+    be.gather_points_grad_wrapper(B, C, N, M, torch.from_numpy(gg).to(DEV), torch.from_numpy(gi).to(DEV), a)
+    np.testing.assert_allclose(a.cpu().numpy(), 2 * oracle.gather_points_grad(gg, gi, N), rtol=2e-5, atol=2e-5)

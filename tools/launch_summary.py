@@ -20,13 +20,12 @@ def main():
     hdr, data = rows[hi], rows[hi + 1:]
     ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
     ls = [(r[ki], float(r[vi].replace(",", ""))) for r in data if len(r) > vi and r[mi] == "gpu__time_duration.sum"]
-    # the last forward = the launches after the last-but-one occurrence pattern: split by the first kernel of a forward
-    if forwards > 1:
-        first = None
-        names = [k for k, _ in ls]
-        # the forward starts with the kernel that occurs exactly `forwards` x c times and appears first in the tail
-        per = len(ls) // forwards
-        ls = ls[len(ls) - per:]
+    # forwards are separated by the marker kernel tools/model_once.py launches (a float64 fill); keep the last one
+    marks = [i for i, (k, _) in enumerate(ls) if "FillFunctor<double>" in k]
+    if marks:
+        ls = ls[marks[-1] + 1:]
+    elif forwards > 1:
+        ls = ls[len(ls) - len(ls) // forwards:]
     agg = collections.OrderedDict()
     for k, v in ls:
         k = re.sub(r"\(.*", "", k)
