@@ -197,7 +197,11 @@ def main():
     torch.backends.cudnn.allow_tf32 = False
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)     # NCCL's environment (NCCL_DEBUG ...) is left exactly as the launcher set it
+        # NCCL's verbosity (NCCL_DEBUG ...) is left exactly as the launcher set it; its log only moves from stdout to
+        # stderr, because NCCL also prints at communicator teardown and at process exit -- after the JSON line, which must
+        # stay the LAST line of stdout
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
