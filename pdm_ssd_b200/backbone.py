@@ -24,6 +24,10 @@ from . import pointnet2_modules
 CHECK_BATCH_INDEX = False
 
 
+# PDMSSDBackbone: sample the next layer's centres on a side stream while the current layer runs its MLP (inference).
+OVERLAP_SAMPLING = True
+
+
 class AttrDict(dict):
     """Minimal EasyDict stand-in (pcdet/config.py uses easydict): attribute access + .get, nested."""
 
@@ -106,11 +110,39 @@ class PDMSSDBackbone(nn.Module):
         self.SA_modules, _, channel_out = _build_sa_chain(model_cfg.SA_CONFIG, input_channels - 3)
         self.num_point_features = channel_out
 
+    def _sample(self, sa, xyz):
+        """FPS + gather of one SA layer (pointnet2_modules.py:28-36), so that a layer can be handed its centres."""
+        from . import pointnet2_utils
+        idx = pointnet2_utils.farthest_point_sample(xyz, sa.npoint)
+        return pointnet2_utils.gather_operation(xyz.transpose(1, 2).contiguous(), idx).transpose(1, 2).contiguous()
+
     def forward(self, batch_dict):
         B = batch_dict['batch_size']
         _, xyz, feats = _split_points(batch_dict['points'], B)
-        for sa in self.SA_modules:
-            xyz, feats = sa(xyz, feats)
+        if xyz.is_cuda and not self.training and OVERLAP_SAMPLING and all(sa.npoint is not None for sa in self.SA_modules):
+            # Layer l+1's sampling needs only layer l's CENTRES, not its features: it runs on a side stream while layer l
+            # does its ball query and shared MLP (a batch's sampling keeps 16 SMs busy, the MLP needs the other 132).
+            # The modules take the centres through their `new_xyz` argument (pointnet2_modules.py:19-23).
+            main = torch.cuda.current_stream(xyz.device)
+            side = self.__dict__.setdefault('_side_stream', {}).get(xyz.device)
+            if side is None:
+                side = self.__dict__['_side_stream'][xyz.device] = torch.cuda.Stream(device=xyz.device)
+            centres = self._sample(self.SA_modules[0], xyz)
+            for li, sa in enumerate(self.SA_modules):
+                nxt = None
+                if li + 1 < len(self.SA_modules):
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        nxt = self._sample(self.SA_modules[li + 1], centres)
+                    nxt.record_stream(main)
+                _, feats = sa(xyz, feats, new_xyz=centres)
+                xyz = centres
+                if nxt is not None:
+                    main.wait_stream(side)
+                    centres = nxt
+        else:
+            for sa in self.SA_modules:
+                xyz, feats = sa(xyz, feats)
         M = xyz.shape[1]
         bcol = torch.arange(B, device=xyz.device, dtype=torch.float32).repeat_interleave(M)[:, None]
         batch_dict['point_coords'] = torch.cat((bcol, xyz.reshape(-1, 3)), dim=1)

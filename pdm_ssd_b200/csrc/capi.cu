@@ -5,6 +5,7 @@
 
 #include <map>
 #include <mutex>
+#include <tuple>
 #include <utility>
 
 #include "common.cuh"
@@ -56,7 +57,7 @@ void prefer_max_smem(const void *func) {
 //   * Eager calls on a stream share one buffer per (device, stream): work on a stream is serialised.  When it has
 //     to grow, the old buffer is released (cudaFree synchronises the device, so nothing can still be using it).
 //   * A call made while its stream is being CAPTURED gets a buffer that belongs to that capture alone (keyed by
-//     the capture id): the first such call adopts the stream's eager buffer -- sized by the warm-up run every
+//     the capture id and the stream -- a capture may fork onto side streams whose work runs concurrently): the first such call adopts the stream's eager buffer -- sized by the warm-up run every
 //     capture needs anyway, allocation is not possible during capture -- and the stream's eager slot is emptied,
 //     so later eager calls, and later captures on the same stream, get a different buffer.  Two graphs therefore
 //     never share scratch, whatever streams they are replayed on (a graph does not run concurrently with itself),
@@ -68,7 +69,7 @@ void *stream_scratch(cudaStream_t st, size_t bytes) {
     struct Buf { void *ptr = nullptr; size_t size = 0; };
     static std::mutex mu;
     static std::map<std::pair<int, cudaStream_t>, Buf> eager;
-    static std::map<std::pair<int, unsigned long long>, Buf> captured;
+    static std::map<std::tuple<int, unsigned long long, cudaStream_t>, Buf> captured;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) { fail(PDM_ERR_INVALID_ARG, "stream_scratch: cudaGetDevice failed"); return nullptr; }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -76,7 +77,7 @@ void *stream_scratch(cudaStream_t st, size_t bytes) {
     if (cudaStreamGetCaptureInfo(st, &cap, &cap_id) != cudaSuccess) { (void)cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
     std::lock_guard<std::mutex> lock(mu);
     if (cap != cudaStreamCaptureStatusNone) {
-        Buf &g = captured[{dev, cap_id}];
+        Buf &g = captured[std::make_tuple(dev, cap_id, st)];   // per stream: a graph may fork onto side streams that run concurrently
         if (!g.ptr) {                       // first scratch user of this capture: adopt the stream's eager buffer
             Buf &e = eager[{dev, st}];
             g = e;
