@@ -362,6 +362,10 @@ def main():
             line["sa_chain"] = sa_chain_record(dev, rank, hbm_peak)
         except Exception as ex:
             line["sa_chain"] = {"error": repr(ex)[:200]}
+        torch.cuda.empty_cache()
+        # the other BASELINE configs, each by its own tool in a child process (bounded; informational sub-records)
+        line["neck_config0"] = tool_record("tools/bench_neck.py", [])                               # configs[0]
+        line["waymo_config4"] = tool_record("tools/bench_waymo.py", ["--batch", "8", "--iters", "2"])   # configs[4], one GPU's share
 
     # ---- CPU baseline: the same detector on this box's host cores, bounded sample ---------------------------------------
     if world == 1 and not args.no_cpu_baseline:
@@ -371,6 +375,18 @@ def main():
                                 "sample": "6 steps x 2 frames of the full detector on CPU (oracle/pdm_model_cpu.py: torch modules + C oracle "
                                           "for the CUDA-only ops), %d threads, %.2f s per step" % (cores, sec)}
     print(json.dumps(line), flush=True)
+
+
+def tool_record(script, argv, timeout=240):
+    """Run one of the per-config tools and return the JSON line it prints (or the error)."""
+    try:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, script)] + argv, capture_output=True, text=True, timeout=timeout)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (out.stderr or out.stdout)[-300:]}
+    except Exception as ex:
+        return {"error": repr(ex)[:200]}
 
 
 def kernel_records(model, dev, pts, hbm_peak, tf_peak):

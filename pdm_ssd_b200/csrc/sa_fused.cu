@@ -12,9 +12,11 @@
 //
 // Arithmetic: fp32 FMA on the CUDA cores (exact to fp32 rounding; the reference runs the same
 // GEMMs in fp32 through cuDNN/cuBLAS with a different summation order, so outputs agree to
-// ~1e-6 relative, far inside the 1e-3 budget).  The layers are genuine GEMMs of shape
-// [128 rows x C_in] x [C_in x C_out] per CTA; a tcgen05 (TF32 / bf16x3) version of the inner
-// product is the planned follow-up -- the data flow stays as is.
+// ~1e-6 relative, far inside the 1e-3 budget).  This file holds the GENERIC kernels of the op --
+// sa_fused_kernel (CUDA cores, any widths <= 128, nsample 4..128) and round 1's tcgen05 kernel
+// (tf32 hi/lo split, one tile per CTA) -- and the dispatch of pdm_sa_fused_forward[_v2]: narrow stacks
+// go to the thread-per-row kernel of sa_rows.cu, GEMM-sized ones to the persistent warp-specialised
+// tcgen05 kernel of sa_tc.cu; what those do not take falls through to the kernels below.
 //
 // Thread tile: 8 rows x 4 output channels, activations stored channel-major A[c][row] so that a
 // thread's 8 rows are two 16-byte shared loads and its 4 weights one 16-byte (broadcast) load per
