@@ -50,7 +50,8 @@ struct ConvTCParams {
     int units_x, units_y, total_units, units_per_cta;
     int nu;              // units per tile: 2 (4 accumulators) when two sets of them fit in TMEM, else 1
     int a_unit_bytes;    // one (unit, plane) box: halo rows x 4 chunks x halo pixels x 16 bytes
-    int w_stage_bytes;   // one (chunk, tap) weight block: 2 planes x 4 chunks x npad rows x 16 bytes
+    int w_block_bytes;   // one (chunk, tap) weight block: 2 planes x 4 chunks x npad rows x 16 bytes
+    int w_stage_bytes;   // one ring stage = the ksize taps of one (chunk, ky) filter row: ksize blocks, contiguous in w_packed
     int a_stages, w_stages;
     int w_resident;      // every weight block has its own slot: loaded once per CTA, never released
     int act;             // 0 none, 1 relu, 2 sigmoid
@@ -97,7 +98,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
     const int u_first = blockIdx.x * P.units_per_cta;
     const int u_last = min(u_first + P.units_per_cta, P.total_units);
     const int n_tiles = (u_last - u_first + NU - 1) / NU;
-    const int n_kc = P.cin / 32, taps = P.ksize * P.ksize, pad = (P.ksize - 1) / 2;
+    const int n_kc = P.cin / 32, pad = (P.ksize - 1) / 2;
 
     if (tid == 0) {
         for (int s = 0; s < P.a_stages; ++s) { mbar_init(cv_smem_u32(&bars.a_full[s]), 1); mbar_init(cv_smem_u32(&bars.a_empty[s]), 1); }
@@ -156,10 +157,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
             const int rounds = P.w_resident ? min(n_tiles, 1) : n_tiles;
             for (int t = 0; t < rounds; ++t) {
                 const unsigned char *src = w_packed;
-                for (int blk = 0; blk < n_kc * taps; ++blk) {
+                for (int rb = 0; rb < n_kc * P.ksize; ++rb) {
                     mbar_wait(cv_smem_u32(&bars.w_empty[stage]), phase ^ 1u, err, 102);
                     const uint32_t full = cv_smem_u32(&bars.w_full[stage]);
-                    if ((P.debug & 2) && (t * n_kc * taps + blk) >= P.w_stages) {
+                    if ((P.debug & 2) && (t * n_kc * P.ksize + rb) >= P.w_stages) {
                         if (elect_one()) mbar_arrive(full);
                         __syncwarp();
                         src += P.w_stage_bytes;
@@ -178,14 +179,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
         }
     } else if (warp == 2) {
         // ===== MMA issuer =====
+        // The issue rate of a single thread is what bounds MMAs with N <= 128 (tools/micro/umma_rate.cu: 64 cycles per
+        // 128x128x16 MMA with loop-invariant descriptors, 80+ as soon as a handful of address instructions sit between
+        // two MMAs).  So: one barrier wait / commit per filter ROW (ksize taps = 36 or 72 MMAs), all of them issued from
+        // one elect region, every descriptor = a per-row base low word + a loop-invariant constant (32-bit adds; the high
+        // words never change).
         {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t H16 = (uint32_t)P.halo * 16u;          // one chunk row of the halo tile
             const uint32_t a_lbo = H16, a_sbo = 4u * H16;
             const uint32_t w_lbo = (uint32_t)P.npad * 16u;
-            const uint32_t w_plane = 4u * w_lbo;
             const uint32_t a_hi_word = cv_desc_hi(a_sbo), w_hi_word = cv_desc_hi(128u);
             const uint32_t a_lbo_f = ((a_lbo >> 4) & 0x3fffu) << 16, w_lbo_f = ((w_lbo >> 4) & 0x3fffu) << 16;
+            // descriptor low-word increments (units of 16 bytes)
+            const uint32_t A_PLANE = (uint32_t)P.a_unit_bytes >> 4, A_UNIT = 2u * A_PLANE, A_KS = (2u * a_lbo) >> 4;
+            const uint32_t W_PLANE = (4u * w_lbo) >> 4, W_KS = (2u * w_lbo) >> 4, W_TAP = (uint32_t)P.w_block_bytes >> 4;
             int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int nun = min(NU, u_last - (u_first + NU * t));
@@ -197,45 +205,44 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(cv_smem_u32(&bars.a_full[as]), aph, err, 104);
                     const uint32_t a_st = a_base + as * a_stage_bytes;
-                    for (int tap = 0; tap < taps; ++tap) {
+                    for (int ky = 0; ky < P.ksize; ++ky) {
                         if (!P.w_resident || t == 0) mbar_wait(cv_smem_u32(&bars.w_full[ws]), wph, err, 105);
                         asm volatile("tcgen05.fence::after_thread_sync;");
-                        const int ky = tap / P.ksize, kx = tap - ky * P.ksize;
-                        const uint32_t w_st = w_base + ws * (uint32_t)P.w_stage_bytes;
-                        const uint64_t wh0 = cv_desc(w_st, w_lbo_f, w_hi_word), wl0 = cv_desc(w_st + w_plane, w_lbo_f, w_hi_word);
-                        const uint64_t wstep = (uint64_t)((2u * w_lbo) >> 4);
-                        for (int un = 0; un < nun; ++un) {
+                        const uint32_t a_row = (((a_st + (uint32_t)ky * a_sbo) >> 4) & 0x3fffu) | a_lbo_f;      // (kx, un, mh, ks, plane) = 0
+                        const uint32_t w_row = (((w_base + ws * (uint32_t)P.w_stage_bytes) >> 4) & 0x3fffu) | w_lbo_f;
+                        const uint32_t first = (uint32_t)((kc | ky) != 0);
+                        if (elect_one()) {
+#pragma unroll 1
+                            for (int un = 0; un < nun; ++un) {
+                                const uint32_t a_un = a_row + (uint32_t)un * A_UNIT;
+                                const uint32_t d_un = acc0 + (uint32_t)(un * 2 * P.npad);
 #pragma unroll
-                            for (int mh = 0; mh < 2; ++mh) {
-                                const uint32_t d = acc0 + (uint32_t)((un * 2 + mh) * P.npad);
-                                const uint32_t a_hi = a_st + (uint32_t)(un * 2) * (uint32_t)P.a_unit_bytes + (uint32_t)ky * a_sbo + (uint32_t)(kx + 8 * mh) * 16u;
-                                const uint64_t ah0 = cv_desc(a_hi, a_lbo_f, a_hi_word);
-                                const uint64_t al0 = cv_desc(a_hi + (uint32_t)P.a_unit_bytes, a_lbo_f, a_hi_word);
-                                const uint64_t astep = (uint64_t)((2u * a_lbo) >> 4);
-                                const uint32_t first = (uint32_t)((kc | tap) != 0);
-                                if (elect_one()) {
-                                    umma_bf16(d, ah0, wh0, idesc, first);
-                                    umma_bf16(d, al0, wh0, idesc, 1);
-                                    umma_bf16(d, ah0, wl0, idesc, 1);
-                                    umma_bf16(d, ah0 + astep, wh0 + wstep, idesc, 1);
-                                    umma_bf16(d, al0 + astep, wh0 + wstep, idesc, 1);
-                                    umma_bf16(d, ah0 + astep, wl0 + wstep, idesc, 1);
+                                for (int kx = 0; kx < 3; ++kx) {
+                                    if (kx < P.ksize) {
+#pragma unroll
+                                        for (int mh = 0; mh < 2; ++mh) {
+                                            const uint32_t d = d_un + (uint32_t)(mh * P.npad);
+#pragma unroll
+                                            for (int ks = 0; ks < 2; ++ks) {
+                                                const uint32_t ah = a_un + (uint32_t)(kx + 8 * mh) + (uint32_t)ks * A_KS;
+                                                const uint32_t wh = w_row + (uint32_t)kx * W_TAP + (uint32_t)ks * W_KS;
+                                                umma_bf16_lohi(d, ah, a_hi_word, wh, w_hi_word, idesc, (kx | ks) ? 1u : first);
+                                                umma_bf16_lohi(d, ah + A_PLANE, a_hi_word, wh, w_hi_word, idesc, 1u);
+                                                umma_bf16_lohi(d, ah, a_hi_word, wh + W_PLANE, w_hi_word, idesc, 1u);
+                                            }
+                                        }
+                                    }
                                 }
-                                __syncwarp();
                             }
+                            if (!P.w_resident) umma_commit(cv_smem_u32(&bars.w_empty[ws]));   // filter row free once these MMAs retire
+                            if (ky + 1 == P.ksize) umma_commit(cv_smem_u32(&bars.a_empty[as]));   // halo chunk free
+                            if (ky + 1 == P.ksize && kc + 1 == n_kc) umma_commit(cv_smem_u32(&bars.acc_full[set]));   // tile complete
                         }
-                        if (!P.w_resident) {
-                            if (elect_one()) umma_commit(cv_smem_u32(&bars.w_empty[ws]));   // weight block free once these MMAs retire
-                            __syncwarp();
-                        }
+                        __syncwarp();
                         if (++ws == P.w_stages) { ws = 0; wph ^= 1u; }
                     }
-                    if (elect_one()) umma_commit(cv_smem_u32(&bars.a_empty[as]));          // halo chunk free
-                    __syncwarp();
                     if (++as == P.a_stages) { as = 0; aph ^= 1u; }
                 }
-                if (elect_one()) umma_commit(cv_smem_u32(&bars.acc_full[set]));            // accumulators of this tile complete
-                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -461,20 +468,21 @@ extern "C" int pdm_conv_tc_forward(int b, int y, int x, int cin, int cout, int k
     P.units_per_cta = per;
     const int grid = (P.total_units + per - 1) / per;
     P.a_unit_bytes = P.halo * 4 * P.halo * 16;
-    P.w_stage_bytes = 2 * 4 * P.npad * 16;
+    P.w_block_bytes = 2 * 4 * P.npad * 16;
+    P.w_stage_bytes = ksize * P.w_block_bytes;
     int cols = 4 * P.nu * P.npad, pw = 32;
     while (pw < cols) pw <<= 1;
     P.tmem_cols = pw;
-    // shared memory: halo ring (2 stages when a tile has two units, else 3), the rest for weight blocks;
-    // if every block of the layer fits they stay resident
+    // shared memory: halo ring (2 stages when a tile has two units, else 3), the rest for filter rows (ksize weight
+    // blocks each); if every row of the layer fits they stay resident
     const int a_stage = 2 * P.nu * P.a_unit_bytes;
-    const int n_blocks = (cin / 32) * ksize * ksize;
+    const int n_rows = (cin / 32) * ksize;
     P.a_stages = P.nu == 2 ? 2 : 3;
     int w_fit = (kCvSmemBudget - P.a_stages * a_stage) / P.w_stage_bytes;
     if (w_fit < 2 && P.a_stages > 2) { P.a_stages = 2; w_fit = (kCvSmemBudget - P.a_stages * a_stage) / P.w_stage_bytes; }
     if (w_fit < 2) return fail(PDM_ERR_UNSUPPORTED, "conv_tc_forward: operands do not fit in shared memory");
-    P.w_resident = (w_fit >= n_blocks && n_blocks <= kCvMaxWStages) ? 1 : 0;
-    P.w_stages = P.w_resident ? n_blocks : (w_fit < 8 ? w_fit : 8);
+    P.w_resident = (w_fit >= n_rows && n_rows <= kCvMaxWStages) ? 1 : 0;
+    P.w_stages = P.w_resident ? n_rows : (w_fit < 4 ? w_fit : 4);
     static const int dbg = [] { const char *e = getenv("PDM_CONV_DEBUG"); return e ? atoi(e) : 0; }();
     P.debug = dbg;
 
