@@ -139,27 +139,28 @@ sa_tc3_kernel(const SATc3Params P, const float *__restrict__ xyz, const float *_
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const int K = P.kpad[l], N = P.npad[l];
                 const uint32_t a_base = l == 0 ? cv_smem_u32(a1_s) + (uint32_t)(st * P.a1_bytes) : cv_smem_u32(a23_s);
-                const uint32_t a_plane = (uint32_t)(K / 8) * kStRows * 16u;
                 const uint32_t w_base = cv_smem_u32(w_s) + (uint32_t)P.woff[l];
-                const uint32_t w_plane = (uint32_t)(K / 8) * (uint32_t)N * 16u;
-                const uint32_t w_lbo_f = ((((uint32_t)N * 16u) >> 4) & 0x3fffu) << 16;
+                // descriptor low words (start address >> 4 | LBO) + constants in units of 16 bytes: below N = 256 the issuing
+                // thread bounds the MMA rate (tools/micro/umma_rate.cu), so nothing but adds sits between two MMAs
+                const uint32_t a_lo0 = ((a_base >> 4) & 0x3fffu) | a_lbo_f;
+                const uint32_t w_lo0 = ((w_base >> 4) & 0x3fffu) | (((((uint32_t)N * 16u) >> 4) & 0x3fffu) << 16);
+                const uint32_t A_PLANE = (uint32_t)(K / 8) * kStRows, W_PLANE = (uint32_t)(K / 8) * (uint32_t)N;   // (bytes >> 4)
+                const uint32_t A_KS = 2u * kStRows, W_KS = 2u * (uint32_t)N;
                 const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(kStRows >> 4) << 24);
                 const uint32_t d = tmem_base + (uint32_t)P.dcol[l];
-                for (int ks = 0; ks < K / 16; ++ks) {
-                    const uint32_t ao = a_base + (uint32_t)ks * 2u * kStRows * 16u, wo = w_base + (uint32_t)ks * 2u * (uint32_t)N * 16u;
-                    const uint64_t a0 = cv_desc(ao, a_lbo_f, a_hi_word), a1 = cv_desc(ao + a_plane, a_lbo_f, a_hi_word), a2 = cv_desc(ao + 2 * a_plane, a_lbo_f, a_hi_word);
-                    const uint64_t w0 = cv_desc(wo, w_lbo_f, w_hi_word), w1 = cv_desc(wo + w_plane, w_lbo_f, w_hi_word), w2 = cv_desc(wo + 2 * w_plane, w_lbo_f, w_hi_word);
-                    const uint32_t first = (uint32_t)(ks != 0);
-                    if (!(P.debug & 8) && elect_one()) {
-                        umma_bf16(d, a0, w0, idesc, first);      // hi*hi
-                        umma_bf16(d, a0, w1, idesc, 1);          // hi*mid
-                        umma_bf16(d, a1, w0, idesc, 1);          // mid*hi
-                        umma_bf16(d, a1, w1, idesc, 1);          // mid*mid
-                        umma_bf16(d, a0, w2, idesc, 1);          // hi*lo
-                        umma_bf16(d, a2, w0, idesc, 1);          // lo*hi
+                if (!(P.debug & 8) && elect_one()) {
+#pragma unroll 1
+                    for (int ks = 0; ks < K / 16; ++ks) {
+                        const uint32_t a0 = a_lo0 + (uint32_t)ks * A_KS, w0 = w_lo0 + (uint32_t)ks * W_KS;
+                        umma_bf16_lohi(d, a0, a_hi_word, w0, w_hi_word, idesc, (uint32_t)(ks != 0));     // hi*hi
+                        umma_bf16_lohi(d, a0, a_hi_word, w0 + W_PLANE, w_hi_word, idesc, 1u);            // hi*mid
+                        umma_bf16_lohi(d, a0 + A_PLANE, a_hi_word, w0, w_hi_word, idesc, 1u);            // mid*hi
+                        umma_bf16_lohi(d, a0 + A_PLANE, a_hi_word, w0 + W_PLANE, w_hi_word, idesc, 1u);  // mid*mid
+                        umma_bf16_lohi(d, a0, a_hi_word, w0 + 2u * W_PLANE, w_hi_word, idesc, 1u);       // hi*lo
+                        umma_bf16_lohi(d, a0 + 2u * A_PLANE, a_hi_word, w0, w_hi_word, idesc, 1u);       // lo*hi
                     }
-                    __syncwarp();
                 }
+                __syncwarp();
                 if (elect_one()) {
                     if (l == 0) umma_commit(cv_smem_u32(&bars.a1_empty[st]));      // gather buffer free once layer 1 retires
                     umma_commit(cv_smem_u32(&bars.d_full[l]));
