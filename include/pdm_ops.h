@@ -284,6 +284,97 @@ int pdm_point_head_forward(int p, int batch, int c_point, int c_bev, int y, int 
 int pdm_sample_points(int b, int total_points, int c, int num_points, unsigned seed, const float *points,
                       const int *counts, float *out, int *choice, void *stream);
 
+/* ---- stacked (ragged-batch) operator family (reference: pcdet/ops/pointnet2/pointnet2_stack) ----------------------
+ * The 15 pybind entries of pointnet2_stack/src/pointnet2_api.cpp:12-31.  Stacked tensors
+ * hold the frames of a batch back to back: xyz (N1+N2+.., 3), features (N1+N2+.., C) channel-last, and a DEVICE int32
+ * array *_batch_cnt (batch) = [N1, N2, ..].  No entry reads a count on the host.  The plain
+ * `farthest_point_sampling_wrapper` of that module (pointnet2_api.cpp:16) is pdm_farthest_point_sampling above. */
+
+/* ball_query_wrapper_stack (pointnet2_api.cpp:13, ball_query.cpp:29-45, ball_query_gpu.cu:15-70).
+ * new_xyz (M,3), xyz (N,3) -> idx (M,nsample): indices LOCAL to the centre's frame, first nsample hits (d2 < r*r) in
+ * ascending order padded with the first; a centre without a hit gets idx[0] = -1 and the rest of its row untouched
+ * (the caller zero-fills, pointnet2_utils.py:31). */
+int pdm_stack_ball_query(int b, int m_total, int n_total, float radius, int nsample, const float *new_xyz,
+                         const int *new_xyz_batch_cnt, const float *xyz, const int *xyz_batch_cnt, int *idx,
+                         void *stream);
+
+/* voxel_query_wrapper_stack (pointnet2_api.cpp:14, voxel_query.cpp:21-41, voxel_query_gpu.cu:10-88).
+ * new_coords (M,4) int32 [batch, z, y, x]; point_indices (B, r1, r2, r3) int32 = row of the point held by a voxel or -1;
+ * xyz (N,3) GLOBAL rows -> idx (M,nsample): the first nsample voxels of the (z,y,x)-ordered neighbourhood whose point
+ * has d2 <= r*r, padded with the first; idx[0] = -1 when there is none. */
+int pdm_stack_voxel_query(int m, int r1, int r2, int r3, int nsample, float radius, int z_range, int y_range,
+                          int x_range, const float *new_xyz, const float *xyz, const int *new_coords,
+                          const int *point_indices, int *idx, void *stream);
+
+/* stack_farthest_point_sampling_wrapper (pointnet2_api.cpp:17, sampling.cpp:37-56, sampling_gpu.cu:263-348).
+ * xyz (N,3), temp (N) pre-filled with 1e10, xyz_batch_cnt (batch), num_sampled_points (batch) ->
+ * idx (sum of num_sampled_points): GLOBAL rows, frame after frame; ties as the reference's 1024-thread tournament. */
+int pdm_stack_farthest_point_sampling(int n_total, int batch, const float *xyz, float *temp, const int *xyz_batch_cnt,
+                                      int *idx, const int *num_sampled_points, void *stream);
+
+/* group_points_wrapper_stack (pointnet2_api.cpp:19, group_points.cpp:50-67, group_points_gpu.cu:67-122).
+ * features (N,C), idx (M,nsample) local indices -> out (M,C,nsample). */
+int pdm_stack_group_points(int b, int m, int c, int nsample, const float *features, const int *features_batch_cnt,
+                           const int *idx, const int *idx_batch_cnt, float *out, void *stream);
+
+/* group_points_grad_wrapper_stack (pointnet2_api.cpp:20, group_points.cpp:29-48, group_points_gpu.cu:14-65).
+ * grad_out (M,C,nsample) -> grad_features (N,C) (+=).  deterministic != 0: in-order sums instead of atomicAdd. */
+int pdm_stack_group_points_grad(int b, int m, int c, int n, int nsample, const float *grad_out, const int *idx,
+                                const int *idx_batch_cnt, const int *features_batch_cnt, float *grad_features,
+                                int deterministic, void *stream);
+
+/* three_nn_wrapper_stack (pointnet2_api.cpp:22, interpolate.cpp:32-60, interpolate_gpu.cu:17-96).
+ * unknown (N,3), known (M,3) -> dist2 (N,3) squared distances, idx (N,3) GLOBAL rows of `known`. */
+int pdm_stack_three_nn(int b, int n, int m, const float *unknown, const int *unknown_batch_cnt, const float *known,
+                       const int *known_batch_cnt, float *dist2, int *idx, void *stream);
+
+/* three_interpolate_wrapper_stack (pointnet2_api.cpp:23, interpolate.cpp:63-83, interpolate_gpu.cu:100-134).
+ * features (M,C), idx (N,3), weight (N,3) -> out (N,C). */
+int pdm_stack_three_interpolate(int n, int c, const float *features, const int *idx, const float *weight, float *out,
+                                void *stream);
+
+/* three_interpolate_grad_wrapper_stack (pointnet2_api.cpp:24, interpolate.cpp:86-106, interpolate_gpu.cu:137-194).
+ * grad_out (N,C) -> grad_features (M,C) (+=). */
+int pdm_stack_three_interpolate_grad(int n, int c, int m, const float *grad_out, const int *idx, const float *weight,
+                                     float *grad_features, int deterministic, void *stream);
+
+/* query_stacked_local_neighbor_idxs_wrapper_stack (pointnet2_api.cpp:26, vector_pool.cpp:27-52,
+ * vector_pool_gpu.cu:98-180).  Per centre the first min(1000, nsample > 0 ? nsample : inf) support points of its frame
+ * inside the ball (neighbor_type 1) or cube of half-size max_neighbour_distance, as GLOBAL rows appended to
+ * stack_neighbor_idxs (capacity avg_length * M); start_len (M,2) = (start, count); *cumsum (device, caller-zeroed) +=
+ * all counts.  Block order in the list is unspecified (atomics, as in the reference). */
+int pdm_stack_query_local_neighbor_idxs(int b, int m, const float *support_xyz, const int *xyz_batch_cnt,
+                                        const float *new_xyz, const int *new_xyz_batch_cnt, int *stack_neighbor_idxs,
+                                        int *start_len, int *cumsum, int avg_length_of_neighbor_idxs,
+                                        float max_neighbour_distance, int nsample, int neighbor_type, void *stream);
+
+/* query_three_nn_by_stacked_local_idxs_wrapper_stack (pointnet2_api.cpp:27, vector_pool.cpp:55-78,
+ * vector_pool_gpu.cu:19-95).  new_xyz_grid_centers (M,G,3) -> idxs (M,G,3) GLOBAL rows (-1: empty list; a missing 2nd /
+ * 3rd neighbour repeats the 1st), dist2 (M,G,3). */
+int pdm_stack_query_three_nn_by_local_idxs(int m, int num_total_grids, const float *support_xyz,
+                                           const float *new_xyz_grid_centers, int *new_xyz_grid_idxs,
+                                           float *new_xyz_grid_dist2, const int *stack_neighbor_idxs,
+                                           const int *start_len, void *stream);
+
+/* vector_pool_wrapper_stack (pointnet2_api.cpp:29, vector_pool.cpp:81-120, vector_pool_gpu.cu:183-373).
+ * Outputs (caller zero-fills, pointnet2_utils.py:397-402): new_features (M, num_c_out) per-cell channel SUMS in
+ * ascending point order, new_local_xyz (M, 3G), point_cnt_of_grid (M,G), grouped_idxs (num_max_sum_points,3) =
+ * (support row, centre row, cell) in unspecified order.  The total number of list entries is left in *cum_sum_device
+ * (a device int the caller reads back -- the reference's launcher does the cudaMemcpy itself, :360). */
+int pdm_stack_vector_pool(int b, int n, int m, int num_c_in, int num_c_out, int num_total_grids,
+                          const float *support_xyz, const int *xyz_batch_cnt, const float *support_features,
+                          const float *new_xyz, const int *new_xyz_batch_cnt, float *new_features,
+                          float *new_local_xyz, int *point_cnt_of_grid, int *grouped_idxs, int num_grid_x,
+                          int num_grid_y, int num_grid_z, float max_neighbour_distance, int use_xyz,
+                          int num_max_sum_points, int nsample, int neighbor_type, int pooling_type,
+                          int *cum_sum_device, void *stream);
+
+/* vector_pool_grad_wrapper_stack (pointnet2_api.cpp:30, vector_pool.cpp:123-147, vector_pool_gpu.cu:376-424).
+ * grad_new_features (M, num_c_out) -> grad_support_features (N, num_c_in) (+=). */
+int pdm_stack_vector_pool_grad(int m, int num_c_out, int n, int num_c_in, int num_total_grids, int num_entries,
+                               const float *grad_new_features, const int *point_cnt_of_grid,
+                               const int *grouped_idxs, float *grad_support_features, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,8 +19,8 @@ _i = ctypes.POINTER(ctypes.c_int)
 
 
 def build(force=False):
-    src = os.path.join(_HERE, "pdm_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, "pdm_oracle.c"), os.path.join(_HERE, "pdm_stack_oracle.c")]
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(s) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libpdm_oracle.so"], stdout=subprocess.DEVNULL)
     return _SO
 

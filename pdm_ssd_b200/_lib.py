@@ -52,6 +52,20 @@ SIGNATURES = {
     "pdm_act_split_from_nchw": [_i, _i, _i, _i, _vp, _vp, _vp],
     "pdm_act_split_to_nchw": [_i, _i, _i, _i, _vp, _vp, _vp],
     "pdm_conv_tc_forward": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _vp, _vp],
+    # stacked family (pointnet2_stack)
+    "pdm_stack_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pdm_stack_voxel_query": [_i, _i, _i, _i, _i, _f, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pdm_stack_farthest_point_sampling": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pdm_stack_group_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pdm_stack_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp],
+    "pdm_stack_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pdm_stack_three_interpolate": [_i, _i, _vp, _vp, _vp, _vp, _vp],
+    "pdm_stack_three_interpolate_grad": [_i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp],
+    "pdm_stack_query_local_neighbor_idxs": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _i, _vp],
+    "pdm_stack_query_three_nn_by_local_idxs": [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
+    "pdm_stack_vector_pool": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _i,
+                              _i, _i, _i, _i, _vp, _vp],
+    "pdm_stack_vector_pool_grad": [_i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp],
 }
 
 _lib = None

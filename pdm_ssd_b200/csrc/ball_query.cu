@@ -85,19 +85,35 @@ __device__ __forceinline__ int bq_cell_coord(float v, float o, float inv, int g)
 
 constexpr int kBuildThreads = 1024;
 
+// Stacked (ragged) frames, pointnet2_stack/src/ball_query_gpu.cu:15-70: frame f owns rows [sum xyz_cnt[:f], +xyz_cnt[f])
+// of xyz and the centres [sum new_cnt[:f], +new_cnt[f]); indices are LOCAL to the frame; a centre without a hit gets
+// idx[0] = -1 (:69).  xyz_cnt == nullptr: uniform (B,N,3) / (B,M,3) frames of the batch API.
+struct BQRagged {
+    const int *xyz_cnt = nullptr, *new_cnt = nullptr;
+    int nframes = 0;
+};
+
 __global__ void __launch_bounds__(kBuildThreads)
 bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQGrid *__restrict__ grids,
-                int *__restrict__ cellid, int *__restrict__ cellend, float4 *__restrict__ sorted) {
+                int *__restrict__ cellid, int *__restrict__ cellend, float4 *__restrict__ sorted,
+                BQRagged rg = BQRagged{}) {
     __shared__ float red[6][kBuildThreads / 32];
     __shared__ BQGrid sg;
     __shared__ int wsum[kBuildThreads / 32];
     __shared__ int carry, tile_total;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int bi = blockIdx.x;
-    const float *pts = xyz + (size_t)bi * n * 3;
-    int *cid = cellid + (size_t)bi * n;
+    size_t pstart = (size_t)bi * n;
+    if (rg.xyz_cnt) {
+        int ps = 0;
+        for (int k = 0; k < bi; ++k) ps += __ldg(rg.xyz_cnt + k);
+        pstart = (size_t)ps;
+        n = __ldg(rg.xyz_cnt + bi);
+    }
+    const float *pts = xyz + pstart * 3;
+    int *cid = cellid + pstart;
     int *cend = cellend + (size_t)bi * cmax;
-    float4 *srt = sorted + (size_t)bi * n;
+    float4 *srt = sorted + pstart;
 
     // 1. frame box over finite coordinates
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -298,27 +314,46 @@ __global__ void __launch_bounds__(kQueryWarps * 32)
 bq_query_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2 /*bitmap words per lane = 1 << wpl_log2*/,
                 const float *__restrict__ new_xyz, const BQGrid *__restrict__ grids,
                 const int *__restrict__ cellend, const float4 *__restrict__ sorted,
-                int *__restrict__ idx) {
+                int *__restrict__ idx, BQRagged rg = BQRagged{}) {
     extern __shared__ unsigned bitmap_all[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int bi = blockIdx.y;
+    int bi = blockIdx.y;
     const int qi = blockIdx.x * (blockDim.x >> 5) + w;   // 8 warps per CTA, fewer when the bitmaps of a large frame need the room
     if (qi >= m) return;  // whole warp
+    size_t xrow0 = (size_t)bi * n, qrow = (size_t)bi * m + qi;
+    if (rg.xyz_cnt) {     // stacked: m = total centres, qi = global centre row; find its frame
+        int acc = 0, ps = 0;
+        bi = 0;
+        for (;;) {
+            const int c = __ldg(rg.new_cnt + bi);
+            if (qi < acc + c || bi == rg.nframes - 1) break;
+            acc += c;
+            ps += __ldg(rg.xyz_cnt + bi);
+            ++bi;
+        }
+        xrow0 = (size_t)ps;
+        qrow = (size_t)qi;
+        n = __ldg(rg.xyz_cnt + bi);
+        if (n <= 0) {     // a frame without points: the empty-ball flag of ball_query_gpu.cu:69
+            if (lane == 0) idx[qrow * nsample] = -1;
+            return;
+        }
+    }
     const int wpl = 1 << wpl_log2;
     const int stride = wpl | 1;  // odd stride: lane-contiguous ownership without bank conflicts
     unsigned *bm = bitmap_all + (size_t)w * 32 * stride;
     unsigned *mine = bm + lane * stride;  // words [lane*wpl, lane*wpl + wpl) of the frame's bitmap
 
     const BQGrid G = grids[bi];
-    const float *q = new_xyz + ((size_t)bi * m + qi) * 3;
+    const float *q = new_xyz + qrow * 3;
     const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
     const int cx = bq_cell_coord(qx, G.ox, G.ix, G.gx);
     const int cy = bq_cell_coord(qy, G.oy, G.iy, G.gy);
     const int cz = bq_cell_coord(qz, G.oz, G.iz, G.gz);
     const int *cend = cellend + (size_t)bi * cmax;
-    const float4 *srt = sorted + (size_t)bi * n;
+    const float4 *srt = sorted + xrow0;
     const int z0 = max(cz - 1, 0), z1 = min(cz + 1, G.gz - 1);
-    int *row = idx + ((size_t)bi * m + qi) * nsample;
+    int *row = idx + qrow * nsample;
 
     // lanes 0..8 fetch the candidate range of their (dx,dy) column
     int rs = 0, re = 0;
@@ -373,7 +408,10 @@ bq_query_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2
         if (hit && slot < 32) bm[slot] = (unsigned)k;
         cnt += __popc(ball);
     }
-    if (cnt == 0) return;  // no hit: the row stays as the caller left it
+    if (cnt == 0) {        // no hit: the row stays as the caller left it (stacked API: empty-ball flag)
+        if (rg.xyz_cnt && lane == 0) row[0] = -1;
+        return;
+    }
     if (cnt <= 32) {
         __syncwarp();
         int v = lane < cnt ? (int)bm[lane] : 0x7fffffff;
@@ -523,11 +561,16 @@ bq_query_tpc_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_
     }
 }
 
+// rg.xyz_cnt != nullptr (stacked API): n / m are the TOTAL row counts of xyz / new_xyz over the b frames
 static int ball_query_grid(int b, int n, int m, float radius, float radius2, int nsample,
-                           const float *new_xyz, const float *xyz, int *idx, cudaStream_t st) {
-    // cells per frame: ~4 per point, power of two, bounded
+                           const float *new_xyz, const float *xyz, int *idx, cudaStream_t st,
+                           BQRagged rg = BQRagged{}) {
+    const bool ragged = rg.xyz_cnt != nullptr;
+    // cells per frame: ~4 per point, power of two, bounded (stacked: sized for twice the mean frame; a larger frame
+    // simply gets wider cells, bq_build_kernel)
+    const long long npf = ragged ? 2LL * (n / b + 1) : n;
     int cmax = 4096;
-    while (cmax < 4 * n && cmax < 262144) cmax <<= 1;
+    while (cmax < 4 * npf && cmax < 262144) cmax <<= 1;
     const int words = (n + 31) / 32;
     int wpl_log2 = 0;  // bitmap words per lane, rounded up to a power of two
     while ((32 << wpl_log2) < words) ++wpl_log2;
@@ -538,9 +581,10 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     if (smem > 200 * 1024) return PDM_ERR_UNSUPPORTED;  // caller falls back to the tiled kernel
 
     const size_t sz_grid = ((sizeof(BQGrid) * b + 255) / 256) * 256;
-    const size_t sz_cid = (((size_t)b * n * sizeof(int) + 255) / 256) * 256;
+    const size_t rows = ragged ? (size_t)n : (size_t)b * n;
+    const size_t sz_cid = ((rows * sizeof(int) + 255) / 256) * 256;
     const size_t sz_cend = (size_t)b * cmax * sizeof(int);
-    const size_t sz_sorted = (size_t)b * n * sizeof(float4);
+    const size_t sz_sorted = rows * sizeof(float4);
     char *scratch = static_cast<char *>(stream_scratch(st, sz_grid + sz_cid + sz_cend + sz_sorted));
     if (!scratch) return PDM_ERR_INVALID_ARG;  // message recorded by stream_scratch
     BQGrid *grids = reinterpret_cast<BQGrid *>(scratch);
@@ -550,7 +594,7 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
 
     prefer_max_smem((const void *)bq_build_kernel);
     prefer_max_smem((const void *)bq_query_kernel);
-    bq_build_kernel<<<b, kBuildThreads, 0, st>>>(n, radius, cmax, xyz, grids, cid, cend, sorted);
+    bq_build_kernel<<<b, kBuildThreads, 0, st>>>(n, radius, cmax, xyz, grids, cid, cend, sorted, rg);
     count_launch();
     cudaError_t e1 = cudaGetLastError();
     if (e1 == cudaSuccess) {
@@ -561,7 +605,7 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
         static const bool warp_kernel = [] { const char *e = getenv("PDM_BQ_KERNEL"); return !(e && e[0] == 't' && e[1] == 'h'); }();
         const size_t smem_tpc = (size_t)(kTpcList + 18) * kTpcStride * sizeof(int) +
                                 (size_t)(kTpcThreads / 32) * 32 * (wpl | 1) * sizeof(unsigned);
-        if (!warp_kernel && smem_tpc <= 100 * 1024 &&
+        if (!warp_kernel && !ragged && smem_tpc <= 100 * 1024 &&
             ensure_dynamic_smem((const void *)bq_query_tpc_kernel, smem_tpc) == PDM_OK) {
             dim3 grid((m + kTpcThreads - 1) / kTpcThreads, b);
             bq_query_tpc_kernel<<<grid, kTpcThreads, smem_tpc, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
@@ -571,9 +615,9 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
         } else {
             if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK)
                 return PDM_ERR_UNSUPPORTED;  // message already recorded; caller falls back to the tiled kernel
-            dim3 grid((m + qwarps - 1) / qwarps, b);
+            dim3 grid((m + qwarps - 1) / qwarps, ragged ? 1 : b);
             bq_query_kernel<<<grid, qwarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
-                                                                 grids, cend, sorted, idx);
+                                                                 grids, cend, sorted, idx, rg);
             count_launch();
             e1 = cudaGetLastError();
         }
@@ -582,7 +626,67 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     return PDM_OK;
 }
 
+// Stacked fallback (unusable radius, or a stack whose bitmaps do not fit): the reference loop itself, one thread per centre.
+__global__ void __launch_bounds__(128)
+ball_query_stack_scan_kernel(int nframes, int m_total, float radius2, int nsample, const float *__restrict__ new_xyz,
+                             const int *__restrict__ new_cnt, const float *__restrict__ xyz,
+                             const int *__restrict__ xyz_cnt, int *__restrict__ idx) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= m_total) return;
+    int bi = 0, acc = 0, ps = 0;
+    for (;;) {
+        const int c = __ldg(new_cnt + bi);
+        if (qi < acc + c || bi == nframes - 1) break;
+        acc += c;
+        ps += __ldg(xyz_cnt + bi);
+        ++bi;
+    }
+    const int n = __ldg(xyz_cnt + bi);
+    const float *pts = xyz + (size_t)ps * 3;
+    const float qx = __ldg(new_xyz + (size_t)qi * 3), qy = __ldg(new_xyz + (size_t)qi * 3 + 1), qz = __ldg(new_xyz + (size_t)qi * 3 + 2);
+    int *row = idx + (size_t)qi * nsample;
+    int cnt = 0;
+    for (int k = 0; k < n; ++k) {
+        const float d2 = sqdist_ref(__fsub_rn(qx, __ldg(pts + (size_t)k * 3)), __fsub_rn(qy, __ldg(pts + (size_t)k * 3 + 1)),
+                                    __fsub_rn(qz, __ldg(pts + (size_t)k * 3 + 2)));
+        if (d2 < radius2) {
+            if (cnt == 0)
+                for (int l = 1; l < nsample; ++l) row[l] = k;
+            row[cnt] = k;
+            if (++cnt >= nsample) break;
+        }
+    }
+    if (cnt == 0) row[0] = -1;
+}
+
 }  // namespace pdm
+
+extern "C" int pdm_stack_ball_query(int b, int m_total, int n_total, float radius, int nsample, const float *new_xyz,
+                                    const int *new_xyz_batch_cnt, const float *xyz, const int *xyz_batch_cnt, int *idx,
+                                    void *stream) {
+    using namespace pdm;
+    if (b < 0 || m_total < 0 || n_total < 0 || nsample < 0) return fail(PDM_ERR_INVALID_ARG, "stack_ball_query: negative size");
+    if (b == 0 || m_total == 0 || nsample == 0) return PDM_OK;
+    if (!new_xyz || !idx || !new_xyz_batch_cnt || !xyz_batch_cnt || (n_total > 0 && !xyz))
+        return fail(PDM_ERR_INVALID_ARG, "stack_ball_query: null pointer");
+    const float radius2 = radius * radius;  // fp32, as pointnet2_stack ball_query_gpu.cu:43
+    cudaStream_t st = (cudaStream_t)stream;
+    const char *force = getenv("PDM_BQ_KERNEL");
+    const bool scan = force && force[0] == 't' && force[1] == 'i';
+    if (!scan && n_total > 0 && radius > 0.f && radius < INFINITY) {
+        BQRagged rg;
+        rg.xyz_cnt = xyz_batch_cnt;
+        rg.new_cnt = new_xyz_batch_cnt;
+        rg.nframes = b;
+        const int rc = ball_query_grid(b, n_total, m_total, radius, radius2, nsample, new_xyz, xyz, idx, st, rg);
+        if (rc != PDM_ERR_UNSUPPORTED) return rc;
+    }
+    ball_query_stack_scan_kernel<<<(m_total + 127) / 128, 128, 0, st>>>(b, m_total, radius2, nsample, new_xyz,
+                                                                       new_xyz_batch_cnt, xyz, xyz_batch_cnt, idx);
+    count_launch();
+    PDM_CHECK_LAUNCH("stack_ball_query");
+    return PDM_OK;
+}
 
 extern "C" int pdm_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                               const float *xyz, int *idx, void *stream) {

@@ -36,22 +36,47 @@
 
 namespace pdm {
 
+// Stacked (ragged) frames, pointnet2_stack/src/sampling_gpu.cu:263-276: frame f owns rows
+// [sum n_cnt[:f], +n_cnt[f]) of xyz / temp and entries [sum m_cnt[:f], +m_cnt[f]) of idx; the sampled
+// indices are GLOBAL rows (local index + frame start).  n_cnt == nullptr: uniform (B,N,3) frames.
+struct FpsRagged {
+    const int *n_cnt = nullptr, *m_cnt = nullptr;
+    int skip_le = 0;      // generic kernel only: frames with n <= skip_le were sampled by the on-chip kernel
+};
+__device__ __forceinline__ bool fps_ragged_frame(const FpsRagged &rg, int f, int &n, int &m, size_t &pstart,
+                                                 size_t &ostart) {
+    int ps = 0, os = 0;
+    for (int k = 0; k < f; ++k) { ps += __ldg(rg.n_cnt + k); os += __ldg(rg.m_cnt + k); }
+    n = __ldg(rg.n_cnt + f);
+    m = __ldg(rg.m_cnt + f);
+    pstart = (size_t)ps;
+    ostart = (size_t)os;
+    return n > 0 && m > 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // generic kernel
 // ---------------------------------------------------------------------------------------
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 fps_generic_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__restrict__ temp,
-                   int *__restrict__ idxs) {
+                   int *__restrict__ idxs, FpsRagged rg = FpsRagged{}) {
     constexpr int NWARP = THREADS / 32;
     __shared__ unsigned long long wbest[2][NWARP];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned bsmask = (1u << p) - 1u;
-    const float *dataset = xyz + (size_t)blockIdx.x * n * 3;
-    float *tmp = temp + (size_t)blockIdx.x * n;
-    int *out = idxs + (size_t)blockIdx.x * m;
+    size_t pstart = (size_t)blockIdx.x * n, ostart = (size_t)blockIdx.x * m;
+    int obase = 0;
+    if (rg.n_cnt) {   // stacked frames (pointnet2_stack): per-frame n, m; indices are global rows
+        if (!fps_ragged_frame(rg, blockIdx.x, n, m, pstart, ostart)) return;
+        if (n <= rg.skip_le) return;     // the on-chip kernel took this frame
+        obase = (int)pstart;
+    }
+    const float *dataset = xyz + pstart * 3;
+    float *tmp = temp + pstart;
+    int *out = idxs + ostart;
     int old = 0;
-    if (tid == 0) out[0] = 0;
+    if (tid == 0) out[0] = obase;
     for (int j = 1; j < m; ++j) {
         const float x1 = __ldg(dataset + old * 3 + 0);
         const float y1 = __ldg(dataset + old * 3 + 1);
@@ -81,7 +106,7 @@ fps_generic_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__
             best = other > best ? other : best;
         }
         old = (int)fps_tiekey_inv(~(unsigned)best, p, bsmask);
-        if (tid == 0) out[j] = old;
+        if (tid == 0) out[j] = old + obase;
     }
 }
 
@@ -185,7 +210,8 @@ __device__ __forceinline__ void reg_store(float (&t)[BPW], int jj, float v) {
 template <int NW, int BPW, int KMAX, bool TRACE = false, int LB = NW * 32>
 __global__ void __launch_bounds__(LB, 1)
 fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__restrict__ temp,
-                  int *__restrict__ idxs, int *__restrict__ stats, long long *__restrict__ trace = nullptr) {
+                  int *__restrict__ idxs, int *__restrict__ stats, long long *__restrict__ trace = nullptr,
+                  FpsRagged rg = FpsRagged{}) {
     using L = FpsSmem<NW, BPW, KMAX>;
     constexpr int CAP = L::CAP;
     constexpr int T = NW * 32;
@@ -201,11 +227,18 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const unsigned bsmask = (1u << p) - 1u;
-    const float *dataset = xyz + (size_t)blockIdx.x * n * 3;
-    float *tmp = temp + (size_t)blockIdx.x * n;
-    int *out = idxs + (size_t)blockIdx.x * m;
+    size_t pstart = (size_t)blockIdx.x * n, ostart = (size_t)blockIdx.x * m;
+    int obase = 0;
+    if (rg.n_cnt) {   // stacked frames (pointnet2_stack): per-frame n, m; indices are global rows
+        if (!fps_ragged_frame(rg, blockIdx.x, n, m, pstart, ostart)) return;
+        if (n > CAP) return;             // left to the any-size kernel (launched next)
+        obase = (int)pstart;
+    }
+    const float *dataset = xyz + pstart * 3;
+    float *tmp = temp + pstart;
+    int *out = idxs + ostart;
 
-    if (tid == 0) out[0] = 0;
+    if (tid == 0) out[0] = obase;
     if (m <= 1) return;
 
     // ---- 1. frame bounding box ----------------------------------------------------------
@@ -433,7 +466,7 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
         PDM_STAMP(3)
         __syncthreads();
         // D. every warp replays the sequential selection on the 2*NW candidates (one per lane)
-        if (w == 0 && pend_slot >= 0) out[pend_slot] = (int)pend_val;
+        if (w == 0 && pend_slot >= 0) out[pend_slot] = (int)pend_val + obase;
         pend_slot = -1;
         const bool live = lane < 2 * NW;
         const uint2 e = live ? pub[par * 2 * NW + lane] : make_uint2(0u, 0u);
@@ -487,7 +520,7 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
             if (K == 0) break;
         }
     }
-    if (w == 0 && pend_slot >= 0) out[pend_slot] = (int)pend_val;
+    if (w == 0 && pend_slot >= 0) out[pend_slot] = (int)pend_val + obase;
     if (stats && tid == 0) stats[blockIdx.x] = rounds;
 
     // ---- 5. leave temp as the reference does: running minima in original order ------------
@@ -513,7 +546,7 @@ static int launch_bucket(int b, int n, int m, int p, const float *xyz, float *te
     auto kern = fps_bucket_kernel<NW, BPW, KMAX, false, LB>;
     if (int rc = ensure_dynamic_smem((const void *)kern, L::kBytes)) return rc;
     prefer_max_smem((const void *)kern);
-    kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, stats, nullptr);
+    kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, stats, nullptr, FpsRagged{});
     count_launch();
     PDM_CHECK_LAUNCH("farthest_point_sampling(bucket)");
     return PDM_OK;
@@ -580,6 +613,59 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
 
 }  // namespace pdm
 
+namespace pdm {
+// stack_farthest_point_sampling_kernel_launcher (pointnet2_stack/src/sampling_gpu.cu:335-348): always the
+// <1024> instantiation, so the tie-break uses block size 1024 (p = 10) whatever the frame sizes are.
+static int fps_stack_dispatch(int n_total, int batch, const float *xyz, float *temp, const int *xyz_cnt, int *idx,
+                              const int *m_cnt, cudaStream_t st) {
+    const int p = 10;
+    FpsRagged rg;
+    rg.n_cnt = xyz_cnt;
+    rg.m_cnt = m_cnt;
+    const char *force = getenv("PDM_FPS_KERNEL");
+    const bool generic = force && force[0] == 'g';
+    int cap = 0;
+    if (!generic) {
+#define PDM_STACK_BUCKET(NWV, BPWV, LBV)                                                            \
+    {                                                                                               \
+        using L = FpsSmem<NWV, BPWV, 8>;                                                            \
+        auto kern = fps_bucket_kernel<NWV, BPWV, 8, false, LBV>;                                    \
+        if (int rc = ensure_dynamic_smem((const void *)kern, L::kBytes)) return rc;                 \
+        prefer_max_smem((const void *)kern);                                                        \
+        kern<<<batch, NWV * 32, L::kBytes, st>>>(0, 0, p, xyz, temp, idx, nullptr, nullptr, rg);    \
+        count_launch();                                                                             \
+        PDM_CHECK_LAUNCH("stack_farthest_point_sampling(bucket)");                                  \
+        cap = L::CAP;                                                                               \
+    }
+        // capacity from the total row count (an upper bound of every frame): small stacks get the small kernels
+        if (n_total <= 2048) PDM_STACK_BUCKET(16, 4, 512)
+        else if (n_total <= 4096) PDM_STACK_BUCKET(16, 8, 512)
+        else if (n_total <= 8192) PDM_STACK_BUCKET(16, 16, 512)
+        else PDM_STACK_BUCKET(16, 32, 544)
+#undef PDM_STACK_BUCKET
+    }
+    if (n_total > cap) {    // some frame may be larger than the on-chip capacity: the any-size kernel takes those
+        rg.skip_le = cap;
+        fps_generic_kernel<1024><<<batch, 1024, 0, st>>>(0, 0, p, xyz, temp, idx, rg);
+        count_launch();
+        PDM_CHECK_LAUNCH("stack_farthest_point_sampling(generic)");
+    }
+    return PDM_OK;
+}
+}  // namespace pdm
+
+extern "C" int pdm_stack_farthest_point_sampling(int n_total, int batch, const float *xyz, float *temp,
+                                                 const int *xyz_batch_cnt, int *idx, const int *num_sampled_points,
+                                                 void *stream) {
+    using namespace pdm;
+    if (n_total < 0 || batch < 0) return fail(PDM_ERR_INVALID_ARG, "stack_farthest_point_sampling: negative size");
+    if (batch == 0 || n_total == 0) return PDM_OK;
+    if (!xyz || !temp || !idx || !xyz_batch_cnt || !num_sampled_points)
+        return fail(PDM_ERR_INVALID_ARG, "stack_farthest_point_sampling: null pointer");
+    if ((long long)n_total * 3 > 0x7fffffffLL) return fail(PDM_ERR_UNSUPPORTED, "stack_farthest_point_sampling: too many rows");
+    return fps_stack_dispatch(n_total, batch, xyz, temp, xyz_batch_cnt, idx, num_sampled_points, (cudaStream_t)stream);
+}
+
 // Debug-only entry: timestamp trace of frame 0 (16384-point frames, <16,32,8> kernel).
 extern "C" int pdm_debug_fps_trace(int b, int n, int m, const float *xyz, float *temp, int *idx,
                                    int *stats, long long *trace, void *stream) {
@@ -590,7 +676,7 @@ extern "C" int pdm_debug_fps_trace(int b, int n, int m, const float *xyz, float 
     using L = FpsSmem<16, 32, 8>;
     auto kern = fps_bucket_kernel<16, 32, 8, true>;
     if (int rc = ensure_dynamic_smem((const void *)kern, L::kBytes)) return rc;
-    kern<<<b, 512, L::kBytes, (cudaStream_t)stream>>>(n, m, p, xyz, temp, idx, stats, trace);
+    kern<<<b, 512, L::kBytes, (cudaStream_t)stream>>>(n, m, p, xyz, temp, idx, stats, trace, FpsRagged{});
     PDM_CHECK_LAUNCH("debug_fps_trace");
     return PDM_OK;
 }
