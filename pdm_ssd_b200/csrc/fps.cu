@@ -134,57 +134,7 @@ struct FpsSmem {
 // lane holds the maximum; equal maxima (duplicate points) are detected with a ballot that runs
 // off the critical path and resolved by the smallest tiekey in a slow path.
 
-// t[jj] for a warp-uniform runtime jj, with t[] in registers.  A 32-way switch around the
-// whole bucket update thrashed the instruction cache (20 KB loop), a flat 32-way select tree
-// costs ~95 half-rate ALU instructions.  So: groups of 8 registers; a (uniform) 2-level branch
-// picks the group, a 3-level select tree (7 FSEL) picks the register inside it.
-template <int W>
-__device__ __forceinline__ float reg_select_tree(const float *t, int jj) {
-    float a[W];
-#pragma unroll
-    for (int i = 0; i < W; ++i) a[i] = t[i];
-#pragma unroll
-    for (int bit = 0; (1 << bit) < W; ++bit) {
-        const bool odd = (jj >> bit) & 1;
-#pragma unroll
-        for (int i = 0; i < (W >> (bit + 1)); ++i) a[i] = odd ? a[2 * i + 1] : a[2 * i];
-    }
-    return a[0];
-}
-template <int BPW>
-__device__ __forceinline__ float reg_select(const float (&t)[BPW], int jj) {
-    if constexpr (BPW <= 8) {
-        return reg_select_tree<BPW>(t, jj);
-    } else {
-        switch (jj >> 3) {
-            case 0: return reg_select_tree<8>(&t[0], jj & 7);
-            case 1: return reg_select_tree<8>(&t[8], jj & 7);
-            case 2: if constexpr (BPW > 16) return reg_select_tree<8>(&t[16], jj & 7);
-            default: if constexpr (BPW > 24) return reg_select_tree<8>(&t[24], jj & 7);
-        }
-        return 0.f;
-    }
-}
-template <int BPW>
-__device__ __forceinline__ void reg_store(float (&t)[BPW], int jj, float v) {
-    if constexpr (BPW <= 8) {
-#pragma unroll
-        for (int q = 0; q < BPW; ++q) t[q] = (q == jj) ? v : t[q];
-    } else {
-        const int r = jj & 7;
-        switch (jj >> 3) {
-#define PDM_GRP(G)                                                         \
-    case G:                                                                \
-        if constexpr (BPW > 8 * G) {                                       \
-            _Pragma("unroll") for (int q = 0; q < 8; ++q) t[8 * G + q] = (q == r) ? v : t[8 * G + q]; \
-        }                                                                  \
-        break;
-            PDM_GRP(0) PDM_GRP(1) PDM_GRP(2) PDM_GRP(3)
-#undef PDM_GRP
-            default: break;
-        }
-    }
-}
+// (reg_select / reg_store: register-array access by a warp-uniform runtime index, fps_common.cuh)
 
 // Multi-sample rounds
 // -------------------
@@ -601,7 +551,12 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
             return launch_bucket<16, 32, 8, 544>(b, n, m, p, xyz, temp, idx, stats, st);
         return launch_cap<16384>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
     }
-    if (!generic && fps_cluster_supports(n)) {   // frames larger than one SM: a cluster of CTAs per frame
+    // frames larger than one SM: a cluster of CTAs per frame, bucket-pruned (PDM_FPS_KERNEL=cluster: the full-sweep version)
+    if (!generic && !(force && force[0] == 'c') && fps_cluster_bucket_supports(n)) {
+        const int rc = fps_cluster_bucket_launch(b, n, m, p, xyz, temp, idx, stats, st);
+        if (rc != PDM_ERR_UNSUPPORTED) return rc;
+    }
+    if (!generic && fps_cluster_supports(n)) {
         const int rc = fps_cluster_launch(b, n, m, p, xyz, temp, idx, st);
         if (rc != PDM_ERR_UNSUPPORTED) return rc;
     }

@@ -178,6 +178,58 @@ __device__ __forceinline__ void fps_sort_keys(unsigned (&v)[E], unsigned *xch, i
     }
 }
 
+// t[jj] for a warp-uniform runtime jj, with t[] in registers.  A 32-way switch around the
+// whole bucket update thrashed the instruction cache (20 KB loop), a flat 32-way select tree
+// costs ~95 half-rate ALU instructions.  So: groups of 8 registers; a (uniform) 2-level branch
+// picks the group, a 3-level select tree (7 FSEL) picks the register inside it.
+template <int W>
+__device__ __forceinline__ float reg_select_tree(const float *t, int jj) {
+    float a[W];
+#pragma unroll
+    for (int i = 0; i < W; ++i) a[i] = t[i];
+#pragma unroll
+    for (int bit = 0; (1 << bit) < W; ++bit) {
+        const bool odd = (jj >> bit) & 1;
+#pragma unroll
+        for (int i = 0; i < (W >> (bit + 1)); ++i) a[i] = odd ? a[2 * i + 1] : a[2 * i];
+    }
+    return a[0];
+}
+template <int BPW>
+__device__ __forceinline__ float reg_select(const float (&t)[BPW], int jj) {
+    if constexpr (BPW <= 8) {
+        return reg_select_tree<BPW>(t, jj);
+    } else {
+        switch (jj >> 3) {
+            case 0: return reg_select_tree<8>(&t[0], jj & 7);
+            case 1: return reg_select_tree<8>(&t[8], jj & 7);
+            case 2: if constexpr (BPW > 16) return reg_select_tree<8>(&t[16], jj & 7);
+            default: if constexpr (BPW > 24) return reg_select_tree<8>(&t[24], jj & 7);
+        }
+        return 0.f;
+    }
+}
+template <int BPW>
+__device__ __forceinline__ void reg_store(float (&t)[BPW], int jj, float v) {
+    if constexpr (BPW <= 8) {
+#pragma unroll
+        for (int q = 0; q < BPW; ++q) t[q] = (q == jj) ? v : t[q];
+    } else {
+        const int r = jj & 7;
+        switch (jj >> 3) {
+#define PDM_GRP(G)                                                         \
+    case G:                                                                \
+        if constexpr (BPW > 8 * G) {                                       \
+            _Pragma("unroll") for (int q = 0; q < 8; ++q) t[8 * G + q] = (q == r) ? v : t[8 * G + q]; \
+        }                                                                  \
+        break;
+            PDM_GRP(0) PDM_GRP(1) PDM_GRP(2) PDM_GRP(3)
+#undef PDM_GRP
+            default: break;
+        }
+    }
+}
+
 // fps_l2.cu: throughput-oriented variant (coordinates stay in L2, several frames per SM).
 // Returns PDM_ERR_UNSUPPORTED (without recording an error) when the shape is outside its range.
 int fps_l2_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st);
@@ -186,5 +238,10 @@ bool fps_l2_supports(int n);
 // fps_cluster.cu: one thread-block cluster per frame for 16384 < n <= 196608 (same convention).
 int fps_cluster_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, cudaStream_t st);
 bool fps_cluster_supports(int n);
+
+
+// fps_cluster_bucket.cu: the same cluster layout with exact bucket pruning and multi-sample rounds (n <= 196608).
+int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st);
+bool fps_cluster_bucket_supports(int n);
 
 }  // namespace pdm

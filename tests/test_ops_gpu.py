@@ -428,6 +428,24 @@ def test_fps_cluster_kernel_vs_oracle(b, n, m):
     assert np.array_equal(got, want) and np.array_equal(got_t, want_t)
 
 
+@pytest.mark.parametrize("b,n,m,cl,kern", [(2, 40000, 3000, 0, ""), (1, 30000, 500, 4, ""), (2, 20000, 257, 16, ""), (2, 33000, 300, 0, "cluster"),
+                                           (9, 163840, 96, 0, "")])
+def test_fps_cluster_bucket_kernel_variants(monkeypatch, b, n, m, cl, kern):
+    """The bucket-pruned cluster kernel (fps_cluster_bucket.cu) with many samples (multi-sample rounds), forced cluster
+    sizes (chunks with long padded tails, 16 small chunks), more frames than resident clusters (two waves), and the
+    full-sweep cluster kernel it replaced (PDM_FPS_KERNEL=cluster), all against the oracle incl. the final scratch."""
+    if cl:
+        monkeypatch.setenv("PDM_FPS_CLUSTER", str(cl))
+    if kern:
+        monkeypatch.setenv("PDM_FPS_KERNEL", kern)
+    rng = np.random.default_rng(n + m)
+    xyz = (rng.uniform(0, 1, (b, n, 3)) * np.array([150.4, 150.4, 6.0]) - np.array([75.2, 75.2, 2.0])).astype(np.float32)
+    xyz[:, n // 2: n // 2 + n // 8] = xyz[:, : n // 8]          # duplicates: exact ties
+    want, want_t = oracle.fps(xyz, m, return_temp=True)
+    got, got_t = our_fps(xyz, m, return_temp=True)
+    assert np.array_equal(got, want) and np.array_equal(got_t, want_t)
+
+
 def test_ball_query_degenerate_inputs():
     rng = np.random.default_rng(4)
     # all points identical; radius larger than the scene; radius tiny; nsample > n; non-finite coordinates
