@@ -11,19 +11,30 @@
 // The reference tests every centre against every point (M*N distance evaluations per frame).
 // Here the points of a frame are first binned into a uniform grid whose cells are at least
 // 1.01 * radius wide (bq_build_kernel: frame box, histogram, exclusive scan, scatter of
-// (x,y,z,k) records -- one CTA per frame).  A centre then only meets the 3x3x3 cells around
-// its own: fp32 rounding of the cell coordinate is ~1e-4 of a cell, far inside the 1% margin,
-// so no point with d2 < r^2 can lie outside that neighbourhood.  bq_query_kernel gives one
-// warp to each centre: the lanes stride over the candidate records (coalesced 16-byte loads),
-// evaluate the exact reference distance, and set bit k of a per-warp bitmap in shared memory
-// for every hit.  The bitmap is then read back in index order, which yields "first nsample
-// hits in ascending k" directly, whatever order the candidates were visited in.
+// (x,y,z,k) records -- one thread-block CLUSTER of up to 8 CTAs per frame, the phases separated by
+// cluster barriers, so a batch of 16 frames builds on 128 SMs in one launch).  A centre then only
+// meets the 3x3x3 cells around its own: fp32 rounding of the cell coordinate is ~1e-4 of a cell, far
+// inside the 1% margin, so no point with d2 < r^2 can lie outside that neighbourhood.
+// bq_query_topk_kernel gives one warp to each centre: the lanes stride over the candidate records
+// (coalesced 16-byte loads), evaluate the exact reference distance, and keep the nsample SMALLEST hit
+// indices in a sorted list held one entry per lane (nsample <= 32) or two (<= 64): a hit below the
+// list's current threshold is inserted with ballot + popc + shfl_up -- no shared memory, no
+// dependence on the frame size, and the list is already in the order the row wants.
+// nsample > 64 keeps the older bitmap kernel (bit k of a per-warp shared-memory bitmap per hit,
+// read back in index order).
 //
 // Tiled kernel (fallback, PDM_BQ_KERNEL=tiled): one thread per centre like the reference,
 // points streamed through shared memory; identical results by construction.
 #include <stdlib.h>
 
+#include <cooperative_groups.h>
+
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pdm {
 
@@ -84,6 +95,24 @@ __device__ __forceinline__ int bq_cell_coord(float v, float o, float inv, int g)
 }
 
 constexpr int kBuildThreads = 1024;
+constexpr int kBuildMaxCl = 8;      // portable cluster size
+constexpr int kBuildAux = 16;       // ints of per-frame build state next to the cell counters (zero-filled by the caller)
+
+// order-preserving float <-> uint map (never 0 for a finite float: 0 means "no value" in the atomics below)
+__device__ __forceinline__ unsigned bq_f2ord(float f) {
+    const unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float bq_ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_nctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// all threads of all CTAs of the cluster; orders global-memory traffic (atomics, stores) before it against loads after it
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // Stacked (ragged) frames, pointnet2_stack/src/ball_query_gpu.cu:15-70: frame f owns rows [sum xyz_cnt[:f], +xyz_cnt[f])
 // of xyz and the centres [sum new_cnt[:f], +new_cnt[f]); indices are LOCAL to the frame; a centre without a hit gets
@@ -93,16 +122,22 @@ struct BQRagged {
     int nframes = 0;
 };
 
+// One cluster of `cl` CTAs (1..8) per frame; CTA `rank` owns a contiguous slice of the frame's points and of its cells.
+// The caller zero-fills the cell counters and the per-slice totals (one memset).  Phases: frame box (every CTA reads
+// the whole frame: cheaper than an exchange + two more cluster barriers) -> histogram of my points (global atomics;
+// totals per cell slice through shared-memory counters) | cluster barrier | exclusive scan of my cell slice | cluster
+// barrier | scatter of my points' (x,y,z,k) records.  No distributed shared memory: the cluster is there for the barriers.
 __global__ void __launch_bounds__(kBuildThreads)
 bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQGrid *__restrict__ grids,
-                int *__restrict__ cellid, int *__restrict__ cellend, float4 *__restrict__ sorted,
-                BQRagged rg = BQRagged{}) {
+                int *__restrict__ cellend, int *__restrict__ parts, float4 *__restrict__ sorted, BQRagged rg) {
     __shared__ float red[6][kBuildThreads / 32];
+    __shared__ int spart[kBuildMaxCl];
     __shared__ BQGrid sg;
     __shared__ int wsum[kBuildThreads / 32];
     __shared__ int carry, tile_total;
+    const int cl = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int bi = blockIdx.x;
+    const int bi = blockIdx.x / cl;
     size_t pstart = (size_t)bi * n;
     if (rg.xyz_cnt) {
         int ps = 0;
@@ -111,13 +146,17 @@ bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQ
         n = __ldg(rg.xyz_cnt + bi);
     }
     const float *pts = xyz + pstart * 3;
-    int *cid = cellid + pstart;
     int *cend = cellend + (size_t)bi * cmax;
+    int *part = parts + (size_t)bi * kBuildAux;                       // [0, 8): slice totals
+    unsigned *fbox = reinterpret_cast<unsigned *>(part + kBuildMaxCl);    // [8, 14): frame box
     float4 *srt = sorted + pstart;
+    const int per = (n + cl - 1) / cl;
+    const int s0 = min(n, rank * per), s1 = min(n, s0 + per);     // my points
 
-    // 1. frame box over finite coordinates
+    // 1. frame box over finite coordinates: my slice, merged through six global atomics (order-preserving uint images;
+    //    the minima are kept as maxima of the complement, so that the caller's zero fill means "nothing yet")
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int k = tid; k < n; k += kBuildThreads) {
+    for (int k = s0 + tid; k < s1; k += kBuildThreads) {
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
             const float v = __ldg(pts + (size_t)k * 3 + a);
@@ -140,16 +179,19 @@ bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQ
         }
     }
     __syncthreads();
+    if (tid < 6) {
+        float v = tid < 3 ? INFINITY : -INFINITY;
+        for (int i = 0; i < kBuildThreads / 32; ++i) v = tid < 3 ? fminf(v, red[tid][i]) : fmaxf(v, red[tid][i]);
+        if (fabsf(v) < INFINITY) atomicMax(fbox + tid, tid < 3 ? ~bq_f2ord(v) : bq_f2ord(v));
+    }
+    cluster_sync_all();
+    if (tid < kBuildMaxCl) spart[tid] = 0;
     if (tid == 0) {
         float l[3], h[3];
         for (int a = 0; a < 3; ++a) {
-            l[a] = INFINITY;
-            h[a] = -INFINITY;
-            for (int i = 0; i < kBuildThreads / 32; ++i) {
-                l[a] = fminf(l[a], red[a][i]);
-                h[a] = fmaxf(h[a], red[3 + a][i]);
-            }
-            if (!(l[a] <= h[a])) l[a] = h[a] = 0.f;  // no finite coordinate on this axis
+            const unsigned wl = __ldcg(fbox + a), wh = __ldcg(fbox + 3 + a);
+            l[a] = wl ? bq_ord2f(~wl) : 0.f;     // no finite coordinate on this axis: 0
+            h[a] = wh ? bq_ord2f(wh) : 0.f;
         }
         // cells at least 1.01 r wide; fewer, wider cells when the frame would need > cmax of them
         const float hmin = radius * 1.01f;
@@ -174,31 +216,37 @@ bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQ
         sg.ix = inv[0]; sg.iy = inv[1]; sg.iz = inv[2];
         sg.gx = g[0]; sg.gy = g[1]; sg.gz = g[2];
         sg.ncell = g[0] * g[1] * g[2];
-        grids[bi] = sg;
-        carry = 0;
+        if (rank == 0) grids[bi] = sg;
     }
     __syncthreads();
     const BQGrid G = sg;
+    const int cpr = ((G.ncell + cl - 1) / cl + 3) / 4 * 4;       // cells per slice
+    const int c_lo = min(G.ncell, rank * cpr), c_hi = min(G.ncell, c_lo + cpr);
 
-    // 2. histogram (global atomics; the counters live in cellend)
-    for (int c = tid; c < G.ncell; c += kBuildThreads) cend[c] = 0;
-    __syncthreads();
-    for (int k = tid; k < n; k += kBuildThreads) {
+    // 2. histogram of my points (the counters live in cellend); totals per cell slice
+    for (int k = s0 + tid; k < s1; k += kBuildThreads) {
         const int cx = bq_cell_coord(__ldg(pts + (size_t)k * 3 + 0), G.ox, G.ix, G.gx);
         const int cy = bq_cell_coord(__ldg(pts + (size_t)k * 3 + 1), G.oy, G.iy, G.gy);
         const int cz = bq_cell_coord(__ldg(pts + (size_t)k * 3 + 2), G.oz, G.iz, G.gz);
         const int c = (cx * G.gy + cy) * G.gz + cz;
-        cid[k] = c;
         atomicAdd(&cend[c], 1);
+        atomicAdd(&spart[c / cpr], 1);
     }
     __syncthreads();
-
-    // 3. exclusive scan of the counts, in place (tiles of 4 * kBuildThreads cells)
-    for (int base = 0; base < G.ncell; base += 4 * kBuildThreads) {
+    if (tid < cl && spart[tid]) atomicAdd(&part[tid], spart[tid]);
+    cluster_sync_all();
+    // 3. exclusive scan of my cell slice, in place
+    if (tid == 0) {
+        int base = 0;
+        for (int i = 0; i < rank; ++i) base += __ldcg(part + i);
+        carry = base;
+    }
+    __syncthreads();
+    for (int base = c_lo; base < c_hi; base += 4 * kBuildThreads) {
         const int c0 = base + tid * 4;
         int v[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (c0 + q < G.ncell) ? cend[c0 + q] : 0;
+        for (int q = 0; q < 4; ++q) v[q] = (c0 + q < c_hi) ? __ldcg(cend + c0 + q) : 0;
         const int tsum = v[0] + v[1] + v[2] + v[3];
         int incl = tsum;
 #pragma unroll
@@ -209,33 +257,34 @@ bq_build_kernel(int n, float radius, int cmax, const float *__restrict__ xyz, BQ
         if (lane == 31) wsum[w] = incl;
         __syncthreads();
         if (w == 0) {
-            int s = wsum[lane];
-            int si = s;
+            int sv = wsum[lane];
+            int si = sv;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int y = __shfl_up_sync(kFullMask, si, o);
                 if (lane >= o) si += y;
             }
-            wsum[lane] = si - s;  // exclusive warp offsets
+            wsum[lane] = si - sv;  // exclusive warp offsets
             if (lane == 31) tile_total = si;
         }
         __syncthreads();
         int run = carry + wsum[w] + incl - tsum;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            if (c0 + q < G.ncell) cend[c0 + q] = run;
+            if (c0 + q < c_hi) cend[c0 + q] = run;
             run += v[q];
         }
         __syncthreads();
         if (tid == 0) carry += tile_total;
         __syncthreads();
     }
-
-    // 4. scatter: the start cursors advance to the (exclusive) ends
-    for (int k = tid; k < n; k += kBuildThreads) {
-        const int slot = atomicAdd(&cend[cid[k]], 1);
-        srt[slot] = make_float4(__ldg(pts + (size_t)k * 3 + 0), __ldg(pts + (size_t)k * 3 + 1),
-                                __ldg(pts + (size_t)k * 3 + 2), __int_as_float(k));
+    cluster_sync_all();
+    // 4. scatter my points: the start cursors advance to the (exclusive) ends
+    for (int k = s0 + tid; k < s1; k += kBuildThreads) {
+        const float x = __ldg(pts + (size_t)k * 3 + 0), y = __ldg(pts + (size_t)k * 3 + 1), z = __ldg(pts + (size_t)k * 3 + 2);
+        const int cx = bq_cell_coord(x, G.ox, G.ix, G.gx), cy = bq_cell_coord(y, G.oy, G.iy, G.gy), cz = bq_cell_coord(z, G.oz, G.iz, G.gz);
+        const int slot = atomicAdd(&cend[(cx * G.gy + cy) * G.gz + cz], 1);
+        srt[slot] = make_float4(x, y, z, __int_as_float(k));
     }
 }
 
@@ -432,133 +481,167 @@ bq_query_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2
 }
 
 // ---------------------------------------------------------------------------------------
-// grid query: one THREAD per centre, crowded centres finished by the warp
+// grid query, nsample <= 64: one warp per centre, the nsample smallest hit indices in registers
 // ---------------------------------------------------------------------------------------
-// (Opt-in experiment, see ball_query_grid.)  The warp-per-centre kernel above spends ~900 warp instructions on a centre (prefix sums, flat
-// candidate walk, sort network -- executed by 32 lanes for ~40 candidates and ~9 hits) and is bound
-// by instruction issue (ncu: 78 % of the issue slots).  Here a thread walks the nine candidate
-// ranges of its own centre (ranges kept in shared memory, records read 16 bytes at a time; a lane's
-// consecutive records share cache lines) and appends the hits to a 32-entry list in shared memory;
-// 87 % of KITTI-shaped SA1 centres have at most 32 hits, which is then the complete hit set: an
-// insertion sort puts it in ascending index order and the warp writes the rows of its 32 centres
-// with coalesced 128-byte stores.  A centre with more than 32 hits stops scanning and is finished
-// by its whole warp with the bitmap pass.  Same results by construction: identical distance
-// arithmetic, "the nsample smallest hit indices in ascending order, padded with the first".
-constexpr int kTpcThreads = 128;
-constexpr int kTpcList = 32;
-constexpr int kTpcStride = kTpcThreads + 1;   // odd row stride: per-thread and per-warp accesses both conflict-free
+// L[r] of lane l = entry 32 r + l of the ascending list (padded with INT_MAX).  Inserting x: its rank is the number of
+// entries below it (ballot + popc); lanes above the rank take their left neighbour's entry (shfl_up), the lane at the
+// rank takes x; the entry pushed out of a full register moves on to the next one.
+template <int R>
+__device__ __forceinline__ void bq_list_insert(int (&L)[R], int x, int lane) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int pos = __popc(__ballot_sync(kFullMask, L[r] < x));
+        if (pos < 32) {                                       // warp-uniform
+            const int last = __shfl_sync(kFullMask, L[r], 31);
+            const int up = __shfl_up_sync(kFullMask, L[r], 1);
+            L[r] = lane < pos ? L[r] : (lane == pos ? x : up);
+            x = last;                                         // moves on (INT_MAX when the register was not full)
+        }
+    }
+}
 
-__global__ void __launch_bounds__(kTpcThreads)
-bq_query_tpc_kernel(int n, int m, float radius2, int nsample, int cmax, int wpl_log2,
-                    const float *__restrict__ new_xyz, const BQGrid *__restrict__ grids,
-                    const int *__restrict__ cellend, const float4 *__restrict__ sorted,
-                    int *__restrict__ idx) {
-    extern __shared__ unsigned tpc_smem[];
-    int *list = reinterpret_cast<int *>(tpc_smem);              // [kTpcList][kTpcStride]
-    int *rs_s = list + kTpcList * kTpcStride;                    // [9][kTpcStride]
-    int *re_s = rs_s + 9 * kTpcStride;                           // [9][kTpcStride]
-    unsigned *bitmap_all = reinterpret_cast<unsigned *>(re_s + 9 * kTpcStride);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int bi = blockIdx.y;
-    const int qi = blockIdx.x * kTpcThreads + tid;
-    const bool live = qi < m;
+template <int R>
+__global__ void __launch_bounds__(256)
+bq_query_topk_kernel(int n, int m, float radius2, int nsample, int cmax, const float *__restrict__ new_xyz,
+                     const BQGrid *__restrict__ grids, const int *__restrict__ cellend,
+                     const float4 *__restrict__ sorted, int *__restrict__ idx, BQRagged rg) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int bi = blockIdx.y;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + w;
+    if (qi >= m) return;  // whole warp
+    size_t xrow0 = (size_t)bi * n, qrow = (size_t)bi * m + qi;
+    if (rg.xyz_cnt) {     // stacked: m = total centres, qi = global centre row; find its frame
+        int acc = 0, ps = 0;
+        bi = 0;
+        for (;;) {
+            const int c = __ldg(rg.new_cnt + bi);
+            if (qi < acc + c || bi == rg.nframes - 1) break;
+            acc += c;
+            ps += __ldg(rg.xyz_cnt + bi);
+            ++bi;
+        }
+        xrow0 = (size_t)ps;
+        qrow = (size_t)qi;
+        if (__ldg(rg.xyz_cnt + bi) <= 0) {     // a frame without points: the empty-ball flag of ball_query_gpu.cu:69
+            if (lane == 0) idx[qrow * nsample] = -1;
+            return;
+        }
+    }
     const BQGrid G = grids[bi];
-    const float *q = new_xyz + ((size_t)bi * m + (live ? qi : 0)) * 3;
+    const float *q = new_xyz + qrow * 3;
     const float qx = __ldg(q), qy = __ldg(q + 1), qz = __ldg(q + 2);
     const int cx = bq_cell_coord(qx, G.ox, G.ix, G.gx);
     const int cy = bq_cell_coord(qy, G.oy, G.iy, G.gy);
     const int cz = bq_cell_coord(qz, G.oz, G.iz, G.gz);
     const int *cend = cellend + (size_t)bi * cmax;
-    const float4 *srt = sorted + (size_t)bi * n;
+    const float4 *srt = sorted + xrow0;
     const int z0 = max(cz - 1, 0), z1 = min(cz + 1, G.gz - 1);
+    int *row = idx + qrow * nsample;
 
-    // candidate ranges of the 3x3 columns (z0..z1 is contiguous in the cell order)
+    // lanes 0..8 fetch the candidate range of their (dx,dy) column; the nine ranges are walked as ONE flat index space
+    int rs = 0, re = 0;
+    if (lane < 9) {
+        const int x = cx + lane / 3 - 1, y = cy + lane % 3 - 1;
+        if (x >= 0 && x < G.gx && y >= 0 && y < G.gy) {
+            const int c0 = (x * G.gy + y) * G.gz + z0;
+            const int c1 = (x * G.gy + y) * G.gz + z1;
+            rs = c0 == 0 ? 0 : __ldg(cend + c0 - 1);
+            re = __ldg(cend + c1);
+        }
+    }
+    int pre = re - rs;  // lengths -> inclusive prefix over lanes 0..8
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) {
+        const int y = __shfl_up_sync(kFullMask, pre, o);
+        if (lane >= o) pre += y;
+    }
+    const int total_cand = __shfl_sync(kFullMask, pre, 8);
+    int pstart[9], rstart[9];
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
-        const int x = cx + r / 3 - 1, y = cy + r % 3 - 1;
-        int s = 0, e = 0;
-        if (live && x >= 0 && x < G.gx && y >= 0 && y < G.gy) {
-            const int c0 = (x * G.gy + y) * G.gz + z0, c1 = (x * G.gy + y) * G.gz + z1;
-            s = c0 == 0 ? 0 : __ldg(cend + c0 - 1);
-            e = __ldg(cend + c1);
-        }
-        rs_s[r * kTpcStride + tid] = s;
-        re_s[r * kTpcStride + tid] = e;
+        pstart[r] = r == 0 ? 0 : __shfl_sync(kFullMask, pre, r - 1);
+        rstart[r] = __shfl_sync(kFullMask, rs, r);
     }
-    int cnt = 0;
-    {
-        // four records in flight per thread: the walk is a chain of dependent L2 reads otherwise
-        constexpr int PF = 4;
-        int r = 0, i = rs_s[tid], end = re_s[tid];
-        bool more = true;
-        while (more) {
-            int ii[PF];
+    auto record_of = [&](int f) -> int {
+        int i = rstart[0] + f;
 #pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                while (i >= end && r < 8) {
-                    ++r;
-                    i = rs_s[r * kTpcStride + tid];
-                    end = re_s[r * kTpcStride + tid];
-                }
-                ii[u] = i < end ? i++ : -1;
-            }
-            if (ii[0] < 0) break;
-            float4 pt[PF];
+        for (int r = 1; r < 9; ++r) i = f >= pstart[r] ? rstart[r] + (f - pstart[r]) : i;
+        return i;
+    };
+
+    int L[R];
 #pragma unroll
-            for (int u = 0; u < PF; ++u) pt[u] = __ldg(srt + max(ii[u], 0));
+    for (int r = 0; r < R; ++r) L[r] = 0x7fffffff;
+    int hits = 0, tau = 0x7fffffff;     // tau: only indices below it can still enter the list
+    const int tr = (nsample - 1) >> 5, tl = (nsample - 1) & 31;     // where entry nsample - 1 lives
+    for (int base = 0; base < total_cand; base += 64) {              // two records in flight per lane
+        const int fa = base + lane, fb = base + 32 + lane;
+        const bool la = fa < total_cand, lb = fb < total_cand;
+        float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+        if (la) pa = __ldg(srt + record_of(fa));
+        if (lb) pb = __ldg(srt + record_of(fb));
+        const bool ha = la && sqdist_ref(__fsub_rn(qx, pa.x), __fsub_rn(qy, pa.y), __fsub_rn(qz, pa.z)) < radius2;
+        const bool hb = lb && sqdist_ref(__fsub_rn(qx, pb.x), __fsub_rn(qy, pb.y), __fsub_rn(qz, pb.z)) < radius2;
+        const int ka = __float_as_int(pa.w), kb = __float_as_int(pb.w);
+        const unsigned balla = __ballot_sync(kFullMask, ha), ballb = __ballot_sync(kFullMask, hb);
+        hits += __popc(balla) + __popc(ballb);
+        unsigned qa = __ballot_sync(kFullMask, ha && ka < tau);
+        while (qa) {
+            const int src = __ffs(qa) - 1;
+            qa &= qa - 1u;
+            bq_list_insert<R>(L, __shfl_sync(kFullMask, ka, src), lane);
+        }
+        unsigned qb = __ballot_sync(kFullMask, hb && kb < tau);
+        while (qb) {
+            const int src = __ffs(qb) - 1;
+            qb &= qb - 1u;
+            bq_list_insert<R>(L, __shfl_sync(kFullMask, kb, src), lane);
+        }
+        if (hits >= nsample) {
 #pragma unroll
-            for (int u = 0; u < PF; ++u) {
-                const float d2 = sqdist_ref(__fsub_rn(qx, pt[u].x), __fsub_rn(qy, pt[u].y), __fsub_rn(qz, pt[u].z));
-                if (ii[u] >= 0 && d2 < radius2 && cnt <= kTpcList) {
-                    if (cnt < kTpcList) list[cnt * kTpcStride + tid] = __float_as_int(pt[u].w);
-                    ++cnt;
-                }
-            }
-            more = ii[PF - 1] >= 0 && cnt <= kTpcList;   // crowded (> 32 hits): the warp takes over below
+            for (int r = 0; r < R; ++r)
+                if (r == tr) tau = __shfl_sync(kFullMask, L[r], tl);
         }
     }
-    const bool crowded = cnt > kTpcList;
-    if (!crowded) {   // insertion sort of my hit list (ascending point index)
-        for (int a = 1; a < cnt; ++a) {
-            const int v = list[a * kTpcStride + tid];
-            int b = a - 1;
-            while (b >= 0) {
-                const int u = list[b * kTpcStride + tid];
-                if (u <= v) break;
-                list[(b + 1) * kTpcStride + tid] = u;
-                --b;
-            }
-            list[(b + 1) * kTpcStride + tid] = v;
-        }
+    if (hits == 0) {        // no hit: the row stays as the caller left it (stacked API: empty-ball flag)
+        if (rg.xyz_cnt && lane == 0) row[0] = -1;
+        return;
     }
-    __syncwarp();
-    const int wbase = tid - lane;                 // first thread of my warp
-    int *rows = idx + ((size_t)bi * m + (qi - lane)) * nsample;   // row of lane 0's centre
-    // rows of the complete lists: one coalesced store per 32 slots
-    unsigned wmask = __ballot_sync(kFullMask, live && !crowded && cnt > 0);
-    while (wmask) {
-        const int c = __ffs(wmask) - 1;
-        wmask &= wmask - 1u;
-        const int cc = __shfl_sync(kFullMask, cnt, c);
-        const int first = list[wbase + c];
-        const int v = lane < cc ? list[lane * kTpcStride + wbase + c] : first;
-        int *row = rows + (size_t)c * nsample;
-        for (int l = lane; l < nsample; l += 32) row[l] = l < cc ? v : first;   // l < cc implies l == lane
+    const int have = min(hits, nsample);
+    const int first = __shfl_sync(kFullMask, L[0], 0);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int l = 32 * r + lane;
+        if (l < nsample) row[l] = l < have ? L[r] : first;
     }
-    // crowded centres: bitmap pass by the whole warp
-    unsigned cmask = __ballot_sync(kFullMask, live && crowded);
-    if (cmask) {
-        unsigned *bm = bitmap_all + (size_t)w * 32 * ((1 << wpl_log2) | 1);
-        while (cmask) {
-            const int c = __ffs(cmask) - 1;
-            cmask &= cmask - 1u;
-            const float cqx = __shfl_sync(kFullMask, qx, c), cqy = __shfl_sync(kFullMask, qy, c), cqz = __shfl_sync(kFullMask, qz, c);
-            const int rs = lane < 9 ? rs_s[lane * kTpcStride + wbase + c] : 0;
-            const int re = lane < 9 ? re_s[lane * kTpcStride + wbase + c] : 0;
-            bq_warp_bitmap_pass(lane, rs, re, cqx, cqy, cqz, radius2, nsample, wpl_log2, bm, srt, rows + (size_t)c * nsample);
-            __syncwarp();
-        }
+}
+
+// clusters of `cl` build CTAs the device keeps resident at once (cached per device and size)
+static int build_active_clusters(int cl) {
+    static std::mutex mu;
+    static std::map<int, int> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(dev * 16 + cl);
+    if (it != cache.end()) return it->second;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cl);
+    cfg.blockDim = dim3(kBuildThreads);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cl;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int v = 0;
+    if (cudaOccupancyMaxActiveClusters(&v, (const void *)bq_build_kernel, &cfg) != cudaSuccess) {
+        (void)cudaGetLastError();
+        v = cl == 1 ? kNumSMs : 0;
     }
+    cache[dev * 16 + cl] = v;
+    return v;
 }
 
 // rg.xyz_cnt != nullptr (stacked API): n / m are the TOTAL row counts of xyz / new_xyz over the b frames
@@ -571,57 +654,81 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     const long long npf = ragged ? 2LL * (n / b + 1) : n;
     int cmax = 4096;
     while (cmax < 4 * npf && cmax < 262144) cmax <<= 1;
+    // lookup kernel: per-warp bitmaps are the cheaper way to order the hits while they are small (n <= 32768: at most 32
+    // words per lane); beyond that -- or never, with PDM_BQ_KERNEL=bitmap / always, with =topk -- the register list
+    const char *kenv = getenv("PDM_BQ_KERNEL");
+    const bool topk = nsample <= 64 && (kenv && kenv[0] == 'b' ? false : (kenv && kenv[0] == 't' && kenv[1] == 'o') ? true : n > 32768);
+    // bitmap kernel only: a warp's bitmap has n bits, large frames get fewer warps per CTA
     const int words = (n + 31) / 32;
-    int wpl_log2 = 0;  // bitmap words per lane, rounded up to a power of two
+    int wpl_log2 = 0;
     while ((32 << wpl_log2) < words) ++wpl_log2;
     const int wpl = 1 << wpl_log2;
-    int qwarps = kQueryWarps;     // a warp's bitmap has n bits: large frames get fewer warps per CTA
+    int qwarps = kQueryWarps;
     while (qwarps > 1 && (size_t)qwarps * 32 * (wpl | 1) * sizeof(unsigned) > 200 * 1024) qwarps >>= 1;
     const size_t smem = (size_t)qwarps * 32 * (wpl | 1) * sizeof(unsigned);
-    if (smem > 200 * 1024) return PDM_ERR_UNSUPPORTED;  // caller falls back to the tiled kernel
+    if (!topk && smem > 200 * 1024) return PDM_ERR_UNSUPPORTED;  // caller falls back to the tiled kernel
 
-    const size_t sz_grid = ((sizeof(BQGrid) * b + 255) / 256) * 256;
     const size_t rows = ragged ? (size_t)n : (size_t)b * n;
-    const size_t sz_cid = ((rows * sizeof(int) + 255) / 256) * 256;
-    const size_t sz_cend = (size_t)b * cmax * sizeof(int);
+    const size_t sz_grid = ((sizeof(BQGrid) * b + 255) / 256) * 256;
+    const size_t sz_cend = ((size_t)b * (cmax + kBuildAux) * sizeof(int) + 255) / 256 * 256;   // counters + per-frame build state
     const size_t sz_sorted = rows * sizeof(float4);
-    char *scratch = static_cast<char *>(stream_scratch(st, sz_grid + sz_cid + sz_cend + sz_sorted));
+    char *scratch = static_cast<char *>(stream_scratch(st, sz_grid + sz_cend + sz_sorted));
     if (!scratch) return PDM_ERR_INVALID_ARG;  // message recorded by stream_scratch
     BQGrid *grids = reinterpret_cast<BQGrid *>(scratch);
-    int *cid = reinterpret_cast<int *>(scratch + sz_grid);
-    int *cend = reinterpret_cast<int *>(scratch + sz_grid + sz_cid);
-    float4 *sorted = reinterpret_cast<float4 *>(scratch + sz_grid + sz_cid + sz_cend);
+    int *cend = reinterpret_cast<int *>(scratch + sz_grid);
+    int *parts = cend + (size_t)b * cmax;
+    float4 *sorted = reinterpret_cast<float4 *>(scratch + sz_grid + sz_cend);
+    PDM_CHECK_CUDA(cudaMemsetAsync(cend, 0, (size_t)b * (cmax + kBuildAux) * sizeof(int), st));
 
-    prefer_max_smem((const void *)bq_build_kernel);
-    prefer_max_smem((const void *)bq_query_kernel);
-    bq_build_kernel<<<b, kBuildThreads, 0, st>>>(n, radius, cmax, xyz, grids, cid, cend, sorted, rg);
-    count_launch();
-    cudaError_t e1 = cudaGetLastError();
-    if (e1 == cudaSuccess) {
-        // thread-per-centre kernel: opt-in (PDM_BQ_KERNEL=thread).  Measured on B200 (SA1, batch 16): 386 us
-        // alone vs 181 us for the warp-per-centre kernel (a thread's walk is a chain of dependent L2 reads
-        // and every warp serialises the bitmap passes of its ~4 crowded centres); the pipelined chain runs
-        // at the same rate with either (44.3k vs 45.7k frames/s), so the warp kernel stays the default.
-        static const bool warp_kernel = [] { const char *e = getenv("PDM_BQ_KERNEL"); return !(e && e[0] == 't' && e[1] == 'h'); }();
-        const size_t smem_tpc = (size_t)(kTpcList + 18) * kTpcStride * sizeof(int) +
-                                (size_t)(kTpcThreads / 32) * 32 * (wpl | 1) * sizeof(unsigned);
-        if (!warp_kernel && !ragged && smem_tpc <= 100 * 1024 &&
-            ensure_dynamic_smem((const void *)bq_query_tpc_kernel, smem_tpc) == PDM_OK) {
-            dim3 grid((m + kTpcThreads - 1) / kTpcThreads, b);
-            bq_query_tpc_kernel<<<grid, kTpcThreads, smem_tpc, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
-                                                                    grids, cend, sorted, idx);
-            count_launch();
-            e1 = cudaGetLastError();
-        } else {
-            if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK)
-                return PDM_ERR_UNSUPPORTED;  // message already recorded; caller falls back to the tiled kernel
-            dim3 grid((m + qwarps - 1) / qwarps, ragged ? 1 : b);
-            bq_query_kernel<<<grid, qwarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz,
-                                                                 grids, cend, sorted, idx, rg);
-            count_launch();
-            e1 = cudaGetLastError();
-        }
+    prefer_max_smem((const void *)bq_build_kernel);     // same L1 / shared split as the rest of the chain (common.cuh)
+    prefer_max_smem((const void *)bq_query_topk_kernel<1>);
+    prefer_max_smem((const void *)bq_query_topk_kernel<2>);
+    // build: a cluster of 1..8 CTAs per frame (>= ~1024 points per CTA): the largest size whose b clusters are all
+    // resident at once (this B200 keeps 15 clusters of 8 such CTAs: a 16-frame batch would run in two waves), else the
+    // one with the fewest waves
+    int cl_hi = (int)((npf + 1023) / 1024);
+    cl_hi = cl_hi < 1 ? 1 : (cl_hi > kBuildMaxCl ? kBuildMaxCl : cl_hi);
+    int cl = 1, best_waves = 1 << 30;
+    for (int c = cl_hi; c >= 1; --c) {
+        const int act = build_active_clusters(c);
+        if (act < 1) continue;
+        const int waves = (b + act - 1) / act;
+        if (waves < best_waves) { best_waves = waves; cl = c; }
+        if (waves == 1) break;
     }
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(b * cl));
+        cfg.blockDim = dim3(kBuildThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, bq_build_kernel, n, radius, cmax, xyz, grids, cend, parts, sorted, rg);
+        if (e != cudaSuccess) return fail((int)e, "ball_query(grid build): %s", cudaGetErrorString(e));
+        count_launch();
+    }
+    if (topk) {
+        dim3 grid((m + 7) / 8, ragged ? 1 : b);
+        if (nsample <= 32)
+            bq_query_topk_kernel<1><<<grid, 256, 0, st>>>(n, m, radius2, nsample, cmax, new_xyz, grids, cend, sorted, idx, rg);
+        else
+            bq_query_topk_kernel<2><<<grid, 256, 0, st>>>(n, m, radius2, nsample, cmax, new_xyz, grids, cend, sorted, idx, rg);
+    } else {
+        prefer_max_smem((const void *)bq_query_kernel);
+        if (smem > 48 * 1024 && ensure_dynamic_smem((const void *)bq_query_kernel, smem) != PDM_OK)
+            return PDM_ERR_UNSUPPORTED;  // message already recorded; caller falls back to the tiled kernel
+        dim3 grid((m + qwarps - 1) / qwarps, ragged ? 1 : b);
+        bq_query_kernel<<<grid, qwarps * 32, smem, st>>>(n, m, radius2, nsample, cmax, wpl_log2, new_xyz, grids, cend, sorted,
+                                                         idx, rg);
+    }
+    count_launch();
+    const cudaError_t e1 = cudaGetLastError();
     if (e1 != cudaSuccess) return fail((int)e1, "ball_query(grid): %s", cudaGetErrorString(e1));
     return PDM_OK;
 }

@@ -417,6 +417,7 @@ int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, floa
         if (chunk > CbL::CAP) break;
         if ((long long)(c - 1) * chunk >= n) continue;      // the last CTA would be empty
         const int act = cb_max_active_clusters(c);
+        if (getenv("PDM_DEBUG_CLUSTER")) fprintf(stderr, "[pdm]   cluster-bucket of %d: %d points per CTA, %d active clusters\n", c, chunk, act);
         if (act < 1) continue;
         const int waves = (b + act - 1) / act;
         if (waves < best_waves) { best_waves = waves; cl = c; cap = chunk; }

@@ -207,15 +207,15 @@ def test_ball_query_golden(path):
 
 
 def test_ball_query_alternative_kernels_agree():
-    """The opt-in kernels (PDM_BQ_KERNEL=thread: thread per centre + warp bitmap pass for crowded centres;
-    =tiled: reference-shaped scan) give the same rows as the default one.  The knob is read once per
-    process, so each variant runs in its own interpreter."""
+    """The other kernels (PDM_BQ_KERNEL=bitmap: the shared-memory bitmap lookup, which also serves nsample > 64;
+    =tiled: reference-shaped scan) give the same rows as the default register top-k lookup.  Each variant runs in its
+    own interpreter."""
     import subprocess, sys
     code = (
         "import numpy as np, torch, sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
         "import oracle; from pdm_ssd_b200 import pointnet2_utils as pu, synthetic;"
         "ok = True\n"
-        "for n, m, r, s in [(16384, 4096, 0.8, 32), (4096, 1024, 1.6, 16), (1000, 37, 2.5, 64)]:\n"
+        "for n, m, r, s in [(16384, 4096, 0.8, 32), (4096, 1024, 1.6, 16), (1000, 37, 2.5, 64), (4096, 512, 3.0, 100)]:\n"
         "    fr = synthetic.kitti_batch(2, n, first_frame=3)[..., :3].copy()\n"
         "    c = oracle.fps(fr, m)\n"
         "    q = np.take_along_axis(fr, c[..., None].astype(np.int64).repeat(3, -1), 1)\n"
@@ -223,7 +223,7 @@ def test_ball_query_alternative_kernels_agree():
         "    ok = ok and np.array_equal(got, oracle.ball_query(r, s, fr, q))\n"
         "print('AGREE' if ok else 'DIFFER')"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
-    for variant in ("thread", "tiled"):
+    for variant in ("bitmap", "tiled"):
         env = dict(os.environ, PDM_BQ_KERNEL=variant)
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]
@@ -231,7 +231,8 @@ def test_ball_query_alternative_kernels_agree():
 
 
 @pytest.mark.parametrize("n,m,r,s", [(4096, 1024, 0.8, 32), (4096, 1024, 1.6, 16), (1000, 37, 2.5, 64),
-                                     (16384, 4096, 0.8, 32), (300, 300, 0.05, 4), (129, 1, 100.0, 200)])
+                                     (16384, 4096, 0.8, 32), (300, 300, 0.05, 4), (129, 1, 100.0, 200), (4096, 777, 2.4, 48),
+                                     (16384, 1024, 3.5, 64), (2048, 2048, 1.0, 33), (5000, 999, 1.2, 1), (4096, 300, 4.0, 128)])
 def test_ball_query_vs_oracle(n, m, r, s):
     fr = synthetic.kitti_batch(2, n, first_frame=n % 5)[..., :3].copy()
     cidx = oracle.fps(fr, m)
