@@ -287,6 +287,27 @@ def main():
     stage_ms = {k: float(np.mean([a.elapsed_time(b) for a, b in v[1:]])) for k, v in stage_ev.items()}
     clocks = sampler.summary() if rank == 0 else None
 
+    # configs[4] at N GPUs: every rank runs the Waymo-scale chain on its own 8 frames at the same time (a child process per
+    # GPU, the same tool as the 1-GPU sub-record); rank 0 aggregates frames over the slowest rank's time
+    waymo_multi = None
+    if world > 1 and not args.no_subrecords:
+        dist.barrier()
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v]
+        mine = tool_record("tools/bench_waymo.py", ["--batch", "8", "--iters", "2"],
+                           env=dict(os.environ, CUDA_VISIBLE_DEVICES=vis[local_rank] if local_rank < len(vis) else str(local_rank)))
+        recs = [None] * world
+        dist.all_gather_object(recs, mine)
+        if rank == 0:
+            ok = [r for r in recs if isinstance(r, dict) and "chain_ms_per_batch" in r]
+            if len(ok) == world:
+                slow = max(r["chain_ms_per_batch"] for r in ok)
+                waymo_multi = {"workload": ok[0]["workload"] + ", per GPU, %d GPUs at once" % world,
+                               "chain_ms_per_batch_max_over_ranks": slow, "chain_frames_per_s": world * 8 / (slow * 1e-3),
+                               "per_rank_chain_ms": [r["chain_ms_per_batch"] for r in ok], "ops_ms_rank0": ok[0]["ops_ms"],
+                               "neck_ms_rank0": ok[0]["neck_ms"]}
+            else:
+                waymo_multi = {"error": [r for r in recs if r not in ok][:1]}
+
     # every collective is behind us: all ranks leave the process group together, rank 0 goes on alone
     if world > 1:
         dist.barrier()
@@ -366,6 +387,8 @@ def main():
         # the other BASELINE configs, each by its own tool in a child process (bounded; informational sub-records)
         line["neck_config0"] = tool_record("tools/bench_neck.py", [])                               # configs[0]
         line["waymo_config4"] = tool_record("tools/bench_waymo.py", ["--batch", "8", "--iters", "2"])   # configs[4], one GPU's share
+    if waymo_multi is not None:
+        line["waymo_config4"] = waymo_multi
 
     # ---- CPU baseline: the same detector on this box's host cores, bounded sample ---------------------------------------
     if world == 1 and not args.no_cpu_baseline:
@@ -377,10 +400,10 @@ def main():
     print(json.dumps(line), flush=True)
 
 
-def tool_record(script, argv, timeout=240):
+def tool_record(script, argv, timeout=240, env=None):
     """Run one of the per-config tools and return the JSON line it prints (or the error)."""
     try:
-        out = subprocess.run([sys.executable, os.path.join(ROOT, script)] + argv, capture_output=True, text=True, timeout=timeout)
+        out = subprocess.run([sys.executable, os.path.join(ROOT, script)] + argv, capture_output=True, text=True, timeout=timeout, env=env)
         for ln in reversed(out.stdout.strip().splitlines()):
             if ln.startswith("{"):
                 return json.loads(ln)

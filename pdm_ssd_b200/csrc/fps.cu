@@ -42,7 +42,13 @@ namespace pdm {
 struct FpsRagged {
     const int *n_cnt = nullptr, *m_cnt = nullptr;
     int skip_le = 0;      // generic kernel only: frames with n <= skip_le were sampled by the on-chip kernel
+    int flags = 0;        // bucket kernel: bit 0 = update surviving buckets two at a time (fps_pair_flag)
 };
+// PDM_FPS_PAIR=0 switches the paired bucket update off (A/B measurements)
+static int fps_pair_flag() {
+    static const int v = [] { const char *e = getenv("PDM_FPS_PAIR"); return (e && e[0] == '0') ? 0 : 1; }();
+    return v;
+}
 __device__ __forceinline__ bool fps_ragged_frame(const FpsRagged &rg, int f, int &n, int &m, size_t &pstart,
                                                  size_t &ostart) {
     int ps = 0, os = 0;
@@ -190,6 +196,7 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
 
     if (tid == 0) out[0] = obase;
     if (m <= 1) return;
+    const bool pair = (rg.flags & 1) != 0;
 
     // ---- 1. frame bounding box ----------------------------------------------------------
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -353,6 +360,54 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
         // B. update the surviving buckets (32 points = 32 lanes each) with the samples that
         //    reach them (usually one)
         while (mask) {
+            if (pair && (mask & (mask - 1u))) {
+                // two surviving buckets at once: their update chains (shuffle -> shared-memory reads -> distance ->
+                // three reductions, ~300 cycles of dependent latency each) are independent and overlap
+                const int j1 = 31 - __clz(mask);
+                mask ^= 1u << j1;
+                const int j2 = 31 - __clz(mask);
+                mask ^= 1u << j2;
+                const unsigned s1 = __shfl_sync(kFull, amask, j1), s2 = __shfl_sync(kFull, amask, j2);
+                const int p1 = j1 * (NW * 32) + wbase, p2 = j2 * (NW * 32) + wbase;
+                const float x1 = sx[p1], y1 = sy[p1], z1 = sz[p1];
+                const float x2 = sx[p2], y2 = sy[p2], z2 = sz[p2];
+                float n1 = reg_select<BPW>(t, j1), n2 = reg_select<BPW>(t, j2);
+                unsigned su = s1 | s2;
+                while (su) {
+                    const int k = 31 - __clz(su);
+                    su ^= 1u << k;
+                    const float4 c = ws[k];
+                    const float d1 = sqdist_ref(__fsub_rn(x1, c.x), __fsub_rn(y1, c.y), __fsub_rn(z1, c.z));
+                    const float d2 = sqdist_ref(__fsub_rn(x2, c.x), __fsub_rn(y2, c.y), __fsub_rn(z2, c.z));
+                    n1 = ((s1 >> k) & 1u) ? fminf(d1, n1) : n1;
+                    n2 = ((s2 >> k) & 1u) ? fminf(d2, n2) : n2;
+                }
+                const unsigned tb1 = __float_as_uint(n1), tb2 = __float_as_uint(n2);
+                const unsigned mx1 = __reduce_max_sync(kFull, tb1), mx2 = __reduce_max_sync(kFull, tb2);
+                const bool h1 = tb1 == mx1, h2 = tb2 == mx2;
+                unsigned wl1 = __reduce_max_sync(kFull, h1 ? (unsigned)lane : 0u), wl2 = __reduce_max_sync(kFull, h2 ? (unsigned)lane : 0u);
+                unsigned sec1 = __reduce_max_sync(kFull, h1 ? 0u : tb1), sec2 = __reduce_max_sync(kFull, h2 ? 0u : tb2);
+                const unsigned bl1 = __ballot_sync(kFull, h1), bl2 = __ballot_sync(kFull, h2);
+                if (multi_bit(bl1)) {
+                    const unsigned cand = h1 ? tiekey_at(p1) : kPadKey;
+                    const unsigned tkm = __reduce_min_sync(kFull, cand);
+                    wl1 = __reduce_max_sync(kFull, cand == tkm ? (unsigned)lane : 0u);
+                    sec1 = mx1;
+                }
+                if (multi_bit(bl2)) {
+                    const unsigned cand = h2 ? tiekey_at(p2) : kPadKey;
+                    const unsigned tkm = __reduce_min_sync(kFull, cand);
+                    wl2 = __reduce_max_sync(kFull, cand == tkm ? (unsigned)lane : 0u);
+                    sec2 = mx2;
+                }
+                if (lane == j1) { bmax = mx1; bwl = wl1; bsec = sec1; }
+                if (lane == j2) { bmax = mx2; bwl = wl2; bsec = sec2; }
+                reg_store<BPW>(t, j1, n1);
+                reg_store<BPW>(t, j2, n2);
+                dirty = true;
+                nupd += 2;
+                continue;
+            }
             const int jj = 31 - __clz(mask);
             mask ^= 1u << jj;
             unsigned smask = __shfl_sync(kFull, amask, jj);
@@ -496,7 +551,9 @@ static int launch_bucket(int b, int n, int m, int p, const float *xyz, float *te
     auto kern = fps_bucket_kernel<NW, BPW, KMAX, false, LB>;
     if (int rc = ensure_dynamic_smem((const void *)kern, L::kBytes)) return rc;
     prefer_max_smem((const void *)kern);
-    kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, stats, nullptr, FpsRagged{});
+    FpsRagged rg0;
+    rg0.flags = fps_pair_flag();
+    kern<<<b, NW * 32, L::kBytes, st>>>(n, m, p, xyz, temp, idx, stats, nullptr, rg0);
     count_launch();
     PDM_CHECK_LAUNCH("farthest_point_sampling(bucket)");
     return PDM_OK;
@@ -577,6 +634,7 @@ static int fps_stack_dispatch(int n_total, int batch, const float *xyz, float *t
     FpsRagged rg;
     rg.n_cnt = xyz_cnt;
     rg.m_cnt = m_cnt;
+    rg.flags = fps_pair_flag();
     const char *force = getenv("PDM_FPS_KERNEL");
     const bool generic = force && force[0] == 'g';
     int cap = 0;
