@@ -32,12 +32,15 @@ constexpr int kCbNW = 16;
 constexpr int kCbT = kCbNW * 32;
 constexpr int kCbSort = 16384;    // keys sorted per CTA (32 per thread); padding sorts last
 
-template <int BPW, int KMAX>
+// SMAP: the position -> frame-index map lives in shared memory (16 B/point: 12288 points per CTA); otherwise in the
+// caller's scratch `temp` (12 B/point on chip: 16384 points per CTA, so a 163840-point frame fits a cluster of 10 and a
+// batch of 8 such frames is resident at once -- this B200 keeps 11 clusters of 10 CTAs but only 7 of 11..16).
+template <int BPW, int KMAX, bool SMAP>
 struct CbSmem {
     static constexpr int CAP = kCbNW * BPW * 32;
-    static_assert(CAP * 16 >= kCbSort * 4, "the sort scratch aliases the coordinate arrays");
+    static_assert(CAP * 12 >= kCbSort * 4, "the sort scratch aliases the coordinate arrays");
     static constexpr size_t kMapOff = (size_t)12 * CAP;                          // pmap[CAP]: frame index of a sorted position
-    static constexpr size_t kPubOff = (size_t)16 * CAP;                          // pub[2][2 NW] uint2 (value bits, position)
+    static constexpr size_t kPubOff = (size_t)(SMAP ? 16 : 12) * CAP;            // pub[2][2 NW] uint2 (value bits, position)
     static constexpr size_t kUOff = kPubOff + sizeof(uint2) * 2 * 2 * kCbNW;     // pubU[2][NW]
     static constexpr size_t kSampOff = ((kUOff + sizeof(unsigned) * 2 * kCbNW + 15) / 16) * 16;   // samp[NW][KMAX] float4
     static constexpr size_t kBoxOff = kSampOff + sizeof(float4) * kCbNW * KMAX;  // box scratch [6 NW]
@@ -45,17 +48,17 @@ struct CbSmem {
     static constexpr size_t kBytes = kCpubOff + sizeof(float4) * 2 * kCbMaxCl * 3;
 };
 
-template <int BPW, int KMAX>
+template <int BPW, int KMAX, bool SMAP>
 __global__ void __launch_bounds__(kCbT, 1)
 fps_cluster_bucket_kernel(int n, int m, int p, int chunk /*points per CTA*/, const float *__restrict__ xyz,
                           float *__restrict__ temp, int *__restrict__ idxs, int *__restrict__ stats) {
-    using L = CbSmem<BPW, KMAX>;
+    using L = CbSmem<BPW, KMAX, SMAP>;
     constexpr int CAP = L::CAP, NW = kCbNW, T = kCbT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *sx = reinterpret_cast<float *>(smem_raw);
     float *sy = sx + CAP;
     float *sz = sy + CAP;
-    unsigned *pmap = reinterpret_cast<unsigned *>(smem_raw + L::kMapOff);
+    unsigned *smap = reinterpret_cast<unsigned *>(smem_raw + L::kMapOff);      // SMAP only
     uint2 *pub = reinterpret_cast<uint2 *>(smem_raw + L::kPubOff);
     unsigned *pubU = reinterpret_cast<unsigned *>(smem_raw + L::kUOff);
     float4 *samp = reinterpret_cast<float4 *>(smem_raw + L::kSampOff);
@@ -74,6 +77,8 @@ fps_cluster_bucket_kernel(int n, int m, int p, int chunk /*points per CTA*/, con
     const int k0 = rank * chunk;
     const int cnt = max(0, min(chunk, n - k0));       // my points: frame indices [k0, k0 + cnt)
     const float *dataset = frame_xyz + (size_t)k0 * 3;
+    unsigned *gmap = reinterpret_cast<unsigned *>(tmp + k0);       // !SMAP: my part of the scratch doubles as the map
+    auto map_get = [&](unsigned pos) -> unsigned { if constexpr (SMAP) return smap[pos]; else return gmap[pos]; };
 
     if (rank == 0 && tid == 0) out[0] = 0;
     if (m <= 1) return;                                // (every CTA of the cluster takes this exit together)
@@ -144,6 +149,7 @@ fps_cluster_bucket_kernel(int n, int m, int p, int chunk /*points per CTA*/, con
         const int pos = ((j * NW + w) << 5) + lane;
         t[j] = pos < cnt ? tmp[k0 + kk_[j]] : 0.f;     // padding: 0 and never the tie winner
     }
+    if constexpr (!SMAP) __syncthreads();              // every initial value is read before the map overwrites the scratch
     float blox = INFINITY, bloy = INFINITY, bloz = INFINITY;
     float bhix = -INFINITY, bhiy = -INFINITY, bhiz = -INFINITY;
     unsigned bmax = 0u, bwl = 0u, bsec = 0u;
@@ -157,7 +163,8 @@ fps_cluster_bucket_kernel(int n, int m, int p, int chunk /*points per CTA*/, con
             y = __ldg(dataset + (size_t)kk_[j] * 3 + 1);
             z = __ldg(dataset + (size_t)kk_[j] * 3 + 2);
         }
-        pmap[pos] = pad ? 0u : (unsigned)(k0 + kk_[j]);
+        if constexpr (SMAP) smap[pos] = pad ? 0u : (unsigned)(k0 + kk_[j]);
+        else if (!pad) gmap[pos] = (unsigned)(k0 + kk_[j]);
         sx[pos] = x;
         sy[pos] = y;
         sz[pos] = z;
@@ -188,7 +195,7 @@ fps_cluster_bucket_kernel(int n, int m, int p, int chunk /*points per CTA*/, con
     const int wbase = (w << 5) + lane;
     const unsigned bbase = (unsigned)(lane * (NW * 32) + (w << 5));
     auto tiekey_at = [&](unsigned pos) -> unsigned {
-        return pos < (unsigned)cnt ? fps_tiekey(pmap[pos], p, bsmask) : kPadKey;
+        return pos < (unsigned)cnt ? fps_tiekey(map_get(pos), p, bsmask) : kPadKey;
     };
     unsigned c1v = 0u, c1p = 0u, c2v = 0u, c2p = 0u, wU = 0u;
     bool dirty = true;
@@ -354,34 +361,41 @@ fps_cluster_bucket_kernel(int n, int m, int p, int chunk /*points per CTA*/, con
     if (stats && tid == 0 && rank == 0) stats[frame] = rounds;
 
     // ---- 5. leave temp as the reference does: running minima in original order
+    unsigned ko[BPW];
 #pragma unroll
     for (int jq = 0; jq < BPW; ++jq) {
         const int pos = ((jq * NW + w) << 5) + lane;
-        if (pos < cnt) tmp[pmap[pos]] = t[jq];
+        ko[jq] = pos < cnt ? map_get(pos) : 0u;
+    }
+    if constexpr (!SMAP) __syncthreads();              // all map entries are read before any of them is overwritten
+#pragma unroll
+    for (int jq = 0; jq < BPW; ++jq) {
+        const int pos = ((jq * NW + w) << 5) + lane;
+        if (pos < cnt) tmp[ko[jq]] = t[jq];
     }
     cluster.sync();   // nobody exits while a peer may still address its shared memory
 }
 
-constexpr int kCbBPW = 24;                       // 16 warps x 24 buckets x 32 points = 12288 points per CTA (192 KB)
 constexpr int kCbKMAX = 8;
-using CbL = CbSmem<kCbBPW, kCbKMAX>;
+using CbLS = CbSmem<24, kCbKMAX, true>;       // 16 warps x 24 buckets x 32 points = 12288 points per CTA, map on chip
+using CbLG = CbSmem<32, kCbKMAX, false>;      // 16384 points per CTA, map in the caller's scratch
 
-bool fps_cluster_bucket_supports(int n) { return n > 16384 && n <= kCbMaxCl * CbL::CAP; }
+bool fps_cluster_bucket_supports(int n) { return n > 16384 && n <= kCbMaxCl * CbLG::CAP; }
 
-static int cb_max_active_clusters(int cl) {
+template <typename Kern>
+static int cb_max_active_clusters(Kern kern, int variant, size_t smem, int cl) {
     static std::mutex mu;
     static std::map<int, int> cache;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     std::lock_guard<std::mutex> lock(mu);
-    const int key = dev * 64 + cl;
+    const int key = (dev * 64 + cl) * 2 + variant;
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
-    auto kern = fps_cluster_bucket_kernel<kCbBPW, kCbKMAX>;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)cl);
     cfg.blockDim = dim3(kCbT);
-    cfg.dynamicSmemBytes = CbL::kBytes;
+    cfg.dynamicSmemBytes = smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl;
@@ -404,29 +418,37 @@ static int cb_max_active_clusters(int cl) {
 // cluster of the needed size; the caller then uses fps_cluster_launch / the any-size kernel.
 int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st) {
     if (!fps_cluster_bucket_supports(n)) return PDM_ERR_UNSUPPORTED;
-    auto kern = fps_cluster_bucket_kernel<kCbBPW, kCbKMAX>;
-    if (int rc = ensure_dynamic_smem((const void *)kern, CbL::kBytes)) return rc;
-    // cluster size: fewest waves first (a batch in ONE wave halves the time), then the most CTAs per frame
-    // (fewer buckets per warp); PDM_FPS_CLUSTER=<size> forces one (testing)
-    const char *fe = getenv("PDM_FPS_CLUSTER");
+    auto kern_s = fps_cluster_bucket_kernel<24, kCbKMAX, true>;
+    auto kern_g = fps_cluster_bucket_kernel<32, kCbKMAX, false>;
+    if (int rc = ensure_dynamic_smem((const void *)kern_s, CbLS::kBytes)) return rc;
+    if (int rc = ensure_dynamic_smem((const void *)kern_g, CbLG::kBytes)) return rc;
+    // (variant, cluster size): fewest waves first (a batch resident in ONE wave halves the time), then the on-chip map,
+    // then the most CTAs per frame (fewer buckets per warp).  PDM_FPS_CLUSTER=<size> / PDM_FPS_CLUSTER_MAP=smem|global
+    // force a choice (testing).
+    const char *fe = getenv("PDM_FPS_CLUSTER"), *me = getenv("PDM_FPS_CLUSTER_MAP");
     const int forced = fe ? atoi(fe) : 0;
-    int cl = 0, cap = 0, best_waves = 1 << 30;
-    for (int c = kCbMaxCl; c >= 2; --c) {
-        if (forced && c != forced) continue;
-        const int chunk = ((n + c - 1) / c + 31) / 32 * 32;
-        if (chunk > CbL::CAP) break;
-        if ((long long)(c - 1) * chunk >= n) continue;      // the last CTA would be empty
-        const int act = cb_max_active_clusters(c);
-        if (getenv("PDM_DEBUG_CLUSTER")) fprintf(stderr, "[pdm]   cluster-bucket of %d: %d points per CTA, %d active clusters\n", c, chunk, act);
-        if (act < 1) continue;
-        const int waves = (b + act - 1) / act;
-        if (waves < best_waves) { best_waves = waves; cl = c; cap = chunk; }
+    const bool dbg = getenv("PDM_DEBUG_CLUSTER") != nullptr;
+    int cl = 0, cap = 0, var = -1, best_waves = 1 << 30;
+    for (int v = 0; v < 2; ++v) {       // 0: map in shared memory, 1: map in global memory
+        if (me && ((me[0] == 's') != (v == 0))) continue;
+        const int vcap = v == 0 ? CbLS::CAP : CbLG::CAP;
+        for (int c = kCbMaxCl; c >= 2; --c) {
+            if (forced && c != forced) continue;
+            const int chunk = ((n + c - 1) / c + 31) / 32 * 32;
+            if (chunk > vcap) break;
+            if ((long long)(c - 1) * chunk >= n) continue;      // the last CTA would be empty
+            const int act = v == 0 ? cb_max_active_clusters(kern_s, 0, CbLS::kBytes, c) : cb_max_active_clusters(kern_g, 1, CbLG::kBytes, c);
+            if (dbg) fprintf(stderr, "[pdm]   cluster-bucket variant %d of %d: %d points per CTA, %d active clusters\n", v, c, chunk, act);
+            if (act < 1) continue;
+            const int waves = (b + act - 1) / act;
+            if (waves < best_waves) { best_waves = waves; cl = c; cap = chunk; var = v; }
+        }
     }
     if (cl == 0) return PDM_ERR_UNSUPPORTED;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b * cl));
     cfg.blockDim = dim3(kCbT);
-    cfg.dynamicSmemBytes = CbL::kBytes;
+    cfg.dynamicSmemBytes = var == 0 ? CbLS::kBytes : CbLG::kBytes;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -435,9 +457,9 @@ int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, floa
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static const bool dbg = getenv("PDM_DEBUG_CLUSTER") != nullptr;
-    if (dbg) fprintf(stderr, "[pdm] fps cluster-bucket: b=%d n=%d cl=%d chunk=%d waves=%d\n", b, n, cl, cap, best_waves);
-    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, n, m, p, cap, xyz, temp, idx, stats);
+    if (dbg) fprintf(stderr, "[pdm] fps cluster-bucket: b=%d n=%d variant=%d cl=%d chunk=%d waves=%d\n", b, n, var, cl, cap, best_waves);
+    const cudaError_t e = var == 0 ? cudaLaunchKernelEx(&cfg, kern_s, n, m, p, cap, xyz, temp, idx, stats)
+                                   : cudaLaunchKernelEx(&cfg, kern_g, n, m, p, cap, xyz, temp, idx, stats);
     if (e != cudaSuccess) return fail((int)e, "farthest_point_sampling(cluster-bucket of %d): %s", cl, cudaGetErrorString(e));
     count_launch();
     return PDM_OK;

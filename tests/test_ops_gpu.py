@@ -430,14 +430,17 @@ def test_fps_cluster_kernel_vs_oracle(b, n, m):
 
 
 @pytest.mark.parametrize("b,n,m,cl,kern", [(2, 40000, 3000, 0, ""), (1, 30000, 500, 4, ""), (2, 20000, 257, 16, ""), (2, 33000, 300, 0, "cluster"),
-                                           (9, 163840, 96, 0, "")])
+                                           (9, 163840, 96, 0, ""), (2, 40000, 2000, 0, "map=global"), (1, 30000, 400, 2, "map=global"),
+                                           (2, 50000, 300, 13, "map=smem"), (8, 163840, 64, 0, "map=smem"), (1, 230000, 40, 0, "")])
 def test_fps_cluster_bucket_kernel_variants(monkeypatch, b, n, m, cl, kern):
     """The bucket-pruned cluster kernel (fps_cluster_bucket.cu) with many samples (multi-sample rounds), forced cluster
     sizes (chunks with long padded tails, 16 small chunks), more frames than resident clusters (two waves), and the
     full-sweep cluster kernel it replaced (PDM_FPS_KERNEL=cluster), all against the oracle incl. the final scratch."""
     if cl:
         monkeypatch.setenv("PDM_FPS_CLUSTER", str(cl))
-    if kern:
+    if kern.startswith("map="):
+        monkeypatch.setenv("PDM_FPS_CLUSTER_MAP", kern[4:])
+    elif kern:
         monkeypatch.setenv("PDM_FPS_KERNEL", kern)
     rng = np.random.default_rng(n + m)
     xyz = (rng.uniform(0, 1, (b, n, 3)) * np.array([150.4, 150.4, 6.0]) - np.array([75.2, 75.2, 2.0])).astype(np.float32)
