@@ -79,6 +79,11 @@ int pdm_gather_points_grad(int b, int c, int n, int npoints, const float *grad_o
  * untouched (the caller zero-fills, pointnet2_utils.py:218). */
 int pdm_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                    const float *xyz, int *idx, void *stream);
+/* The same query with the scheduling mode of the caller given per call (PDM_FPS_MODE_*; results do not depend on it):
+ * LATENCY / AUTO build the lookup grid with a cluster of CTAs per frame (shortest time for a batch alone),
+ * THROUGHPUT with one CTA per frame (no co-scheduling constraint: best when many batches are in flight). */
+int pdm_ball_query_ex(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                      const float *xyz, int *idx, int mode, void *stream);
 
 /* group_points_wrapper (pointnet2_api.cpp:14, group_points.cpp:27-37, group_points_gpu.cu:53-92).
  * points (B,C,N), idx (B,npoints,nsample) -> out (B,C,npoints,nsample). */

@@ -24,6 +24,7 @@ SIGNATURES = {
     "pdm_gather_points": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pdm_gather_points_grad": [_i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pdm_ball_query": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _vp],
+    "pdm_ball_query_ex": [_i, _i, _i, _f, _i, _vp, _vp, _vp, _i, _vp],
     "pdm_group_points": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pdm_group_points_grad": [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp],
     "pdm_three_nn": [_i, _i, _i, _vp, _vp, _vp, _vp, _vp],

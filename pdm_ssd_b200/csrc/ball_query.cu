@@ -647,7 +647,7 @@ static int build_active_clusters(int cl) {
 // rg.xyz_cnt != nullptr (stacked API): n / m are the TOTAL row counts of xyz / new_xyz over the b frames
 static int ball_query_grid(int b, int n, int m, float radius, float radius2, int nsample,
                            const float *new_xyz, const float *xyz, int *idx, cudaStream_t st,
-                           BQRagged rg = BQRagged{}) {
+                           BQRagged rg = BQRagged{}, int mode = PDM_FPS_MODE_AUTO) {
     const bool ragged = rg.xyz_cnt != nullptr;
     // cells per frame: ~4 per point, power of two, bounded (stacked: sized for twice the mean frame; a larger frame
     // simply gets wider cells, bq_build_kernel)
@@ -688,6 +688,14 @@ static int ball_query_grid(int b, int n, int m, float radius, float radius2, int
     // one with the fewest waves
     int cl_hi = (int)((npf + 1023) / 1024);
     cl_hi = cl_hi < 1 ? 1 : (cl_hi > kBuildMaxCl ? kBuildMaxCl : cl_hi);
+    // throughput mode (many batches in flight on several streams): one CTA per frame.  A cluster needs that many SMs of
+    // one GPC free at the same moment, which a busy GPU rarely offers: measured 41.2k frames/s with clusters of 6 against
+    // 47.7k with single CTAs in the pipelined SA chain, and the reverse for a batch alone (2.79 vs 2.86 ms per step).
+    if (mode == PDM_FPS_MODE_THROUGHPUT) cl_hi = 1;
+    if (const char *ce = getenv("PDM_BQ_BUILD_CL")) {      // A/B knob
+        const int f = atoi(ce);
+        if (f >= 1 && f < cl_hi) cl_hi = f;
+    }
     int cl = 1, best_waves = 1 << 30;
     for (int c = cl_hi; c >= 1; --c) {
         const int act = build_active_clusters(c);
@@ -797,6 +805,11 @@ extern "C" int pdm_stack_ball_query(int b, int m_total, int n_total, float radiu
 
 extern "C" int pdm_ball_query(int b, int n, int m, float radius, int nsample, const float *new_xyz,
                               const float *xyz, int *idx, void *stream) {
+    return pdm_ball_query_ex(b, n, m, radius, nsample, new_xyz, xyz, idx, PDM_FPS_MODE_AUTO, stream);
+}
+
+extern "C" int pdm_ball_query_ex(int b, int n, int m, float radius, int nsample, const float *new_xyz,
+                                 const float *xyz, int *idx, int mode, void *stream) {
     using namespace pdm;
     if (b < 0 || n < 0 || m < 0 || nsample < 0) return fail(PDM_ERR_INVALID_ARG, "ball_query: negative size");
     if (b == 0 || m == 0 || nsample == 0 || n == 0) return PDM_OK;
@@ -809,7 +822,7 @@ extern "C" int pdm_ball_query(int b, int n, int m, float radius, int nsample, co
     // the grid needs a usable radius; NaN / non-positive radii have no hits at all or are
     // handled by the scan kernel with the reference's exact comparison
     if (!tiled && radius > 0.f && radius < INFINITY) {
-        const int rc = ball_query_grid(b, n, m, radius, radius2, nsample, new_xyz, xyz, idx, st);
+        const int rc = ball_query_grid(b, n, m, radius, radius2, nsample, new_xyz, xyz, idx, st, BQRagged{}, mode);
         if (rc != PDM_ERR_UNSUPPORTED) return rc;
     }
     dim3 grid((m + 127) / 128, b);

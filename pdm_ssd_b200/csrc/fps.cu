@@ -591,6 +591,10 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
     const bool want_l2 = force ? force[0] == 'l' : (mode == PDM_FPS_MODE_THROUGHPUT || (mode == PDM_FPS_MODE_AUTO && b > kNumSMs));
     static const int l2_min_n = [] { const char *e = getenv("PDM_FPS_L2_MIN_N"); return e ? atoi(e) : 0; }();
     if (!generic && want_l2 && n >= l2_min_n && fps_l2_supports(n)) return fps_l2_launch(b, n, m, p, xyz, temp, idx, stats, st);
+    if (force && force[0] == 'c' && force[1] == 'b') {      // experiment: a cluster per KITTI-sized frame
+        const int rc = fps_cluster_bucket_launch(b, n, m, p, xyz, temp, idx, stats, st, true);
+        if (rc != PDM_ERR_UNSUPPORTED) return rc;
+    }
     if (!generic && n >= 512 && n <= 16384) {
         // warps per CTA / samples per round: tuned on B200; PDM_FPS_NW / PDM_FPS_KMAX override
         const char *nwenv = getenv("PDM_FPS_NW"), *kenv = getenv("PDM_FPS_KMAX");
@@ -609,7 +613,7 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         return launch_cap<16384>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
     }
     // frames larger than one SM: a cluster of CTAs per frame, bucket-pruned (PDM_FPS_KERNEL=cluster: the full-sweep version)
-    if (!generic && !(force && force[0] == 'c') && fps_cluster_bucket_supports(n)) {
+    if (!generic && !(force && force[0] == 'c' && force[1] == 'l') && fps_cluster_bucket_supports(n)) {
         const int rc = fps_cluster_bucket_launch(b, n, m, p, xyz, temp, idx, stats, st);
         if (rc != PDM_ERR_UNSUPPORTED) return rc;
     }

@@ -30,7 +30,7 @@ namespace pdm {
 constexpr int kCbMaxCl = 16;
 constexpr int kCbNW = 16;
 constexpr int kCbT = kCbNW * 32;
-constexpr int kCbSort = 16384;    // keys sorted per CTA (32 per thread); padding sorts last
+constexpr int cb_pow2(int v) { return v <= 1 ? 1 : 2 * cb_pow2((v + 1) / 2); }   // keys sorted per thread: next power of two >= BPW
 
 // SMAP: the position -> frame-index map lives in shared memory (16 B/point: 12288 points per CTA); otherwise in the
 // caller's scratch `temp` (12 B/point on chip: 16384 points per CTA, so a 163840-point frame fits a cluster of 10 and a
@@ -38,7 +38,8 @@ constexpr int kCbSort = 16384;    // keys sorted per CTA (32 per thread); paddin
 template <int BPW, int KMAX, bool SMAP>
 struct CbSmem {
     static constexpr int CAP = kCbNW * BPW * 32;
-    static_assert(CAP * 12 >= kCbSort * 4, "the sort scratch aliases the coordinate arrays");
+    static constexpr int kSortE = cb_pow2(BPW) < 2 ? 2 : cb_pow2(BPW);               // keys sorted per thread (padding sorts last)
+    static_assert((size_t)CAP * 12 >= (size_t)kSortE * kCbT * 4, "the sort scratch aliases the coordinate arrays");
     static constexpr size_t kMapOff = (size_t)12 * CAP;                          // pmap[CAP]: frame index of a sorted position
     static constexpr size_t kPubOff = (size_t)(SMAP ? 16 : 12) * CAP;            // pub[2][2 NW] uint2 (value bits, position)
     static constexpr size_t kUOff = kPubOff + sizeof(uint2) * 2 * 2 * kCbNW;     // pubU[2][NW]
@@ -116,10 +117,10 @@ fps_cluster_bucket_kernel(int n, int m, int p, int chunk /*points per CTA*/, con
     FpsCurve curve;
     curve.init(lo, hi);
 
-    // ---- 2. sort the chunk along the curve: 32 keys per thread (18-bit code | 14-bit local index), padding last
+    // ---- 2. sort the chunk along the curve: E keys per thread (18-bit code | 14-bit local index), padding last
     unsigned *skeys = reinterpret_cast<unsigned *>(smem_raw);
     {
-        constexpr int E = kCbSort / T;
+        constexpr int E = L::kSortE;
         unsigned v[E];
 #pragma unroll
         for (int r = 0; r < E; ++r) {
@@ -377,25 +378,39 @@ fps_cluster_bucket_kernel(int n, int m, int p, int chunk /*points per CTA*/, con
 }
 
 constexpr int kCbKMAX = 8;
-using CbLS = CbSmem<24, kCbKMAX, true>;       // 16 warps x 24 buckets x 32 points = 12288 points per CTA, map on chip
-using CbLG = CbSmem<32, kCbKMAX, false>;      // 16384 points per CTA, map in the caller's scratch
+using CbKern = void (*)(int, int, int, int, const float *, float *, int *, int *);
+struct CbVariant {
+    CbKern kern;
+    int cap;          // points per CTA
+    size_t smem;
+    bool smap;        // index map on chip
+};
+// 16 warps x BPW buckets x 32 points per CTA.  The small ones serve frames of <= 16384 points spread over a cluster
+// (latency mode of the KITTI-sized layers, PDM_FPS_KERNEL=cb); 24: map on chip, 32: map in the caller's scratch.
+static const CbVariant kCbVariants[] = {
+    {fps_cluster_bucket_kernel<4, kCbKMAX, true>, CbSmem<4, kCbKMAX, true>::CAP, CbSmem<4, kCbKMAX, true>::kBytes, true},
+    {fps_cluster_bucket_kernel<8, kCbKMAX, true>, CbSmem<8, kCbKMAX, true>::CAP, CbSmem<8, kCbKMAX, true>::kBytes, true},
+    {fps_cluster_bucket_kernel<24, kCbKMAX, true>, CbSmem<24, kCbKMAX, true>::CAP, CbSmem<24, kCbKMAX, true>::kBytes, true},
+    {fps_cluster_bucket_kernel<32, kCbKMAX, false>, CbSmem<32, kCbKMAX, false>::CAP, CbSmem<32, kCbKMAX, false>::kBytes, false},
+};
+constexpr int kCbNumVariants = 4;
 
-bool fps_cluster_bucket_supports(int n) { return n > 16384 && n <= kCbMaxCl * CbLG::CAP; }
+bool fps_cluster_bucket_supports(int n) { return n > 16384 && n <= kCbMaxCl * kCbVariants[kCbNumVariants - 1].cap; }
 
-template <typename Kern>
-static int cb_max_active_clusters(Kern kern, int variant, size_t smem, int cl) {
+static int cb_max_active_clusters(int variant, int cl) {
     static std::mutex mu;
     static std::map<int, int> cache;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     std::lock_guard<std::mutex> lock(mu);
-    const int key = (dev * 64 + cl) * 2 + variant;
+    const int key = (dev * 64 + cl) * 8 + variant;
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
+    const CbVariant &V = kCbVariants[variant];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)cl);
     cfg.blockDim = dim3(kCbT);
-    cfg.dynamicSmemBytes = smem;
+    cfg.dynamicSmemBytes = V.smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cl;
@@ -404,9 +419,9 @@ static int cb_max_active_clusters(Kern kern, int variant, size_t smem, int cl) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     int v = 0;
-    if (cl > 8 && cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
+    if (cl > 8 && cudaFuncSetAttribute((const void *)V.kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess)
         (void)cudaGetLastError();
-    if (cudaOccupancyMaxActiveClusters(&v, (const void *)kern, &cfg) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveClusters(&v, (const void *)V.kern, &cfg) != cudaSuccess) {
         (void)cudaGetLastError();
         v = 0;
     }
@@ -415,13 +430,11 @@ static int cb_max_active_clusters(Kern kern, int variant, size_t smem, int cl) {
 }
 
 // Returns PDM_ERR_UNSUPPORTED (no error recorded) when the shape is out of range or the device cannot co-schedule a
-// cluster of the needed size; the caller then uses fps_cluster_launch / the any-size kernel.
-int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st) {
-    if (!fps_cluster_bucket_supports(n)) return PDM_ERR_UNSUPPORTED;
-    auto kern_s = fps_cluster_bucket_kernel<24, kCbKMAX, true>;
-    auto kern_g = fps_cluster_bucket_kernel<32, kCbKMAX, false>;
-    if (int rc = ensure_dynamic_smem((const void *)kern_s, CbLS::kBytes)) return rc;
-    if (int rc = ensure_dynamic_smem((const void *)kern_g, CbLG::kBytes)) return rc;
+// cluster of the needed size; the caller then uses fps_cluster_launch / the any-size kernel.  `small_ok`: also take
+// frames of <= 16384 points (one CTA would do; the cluster shortens a round).
+int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st,
+                              bool small_ok) {
+    if (!(fps_cluster_bucket_supports(n) || (small_ok && n >= 2048 && n <= 16384))) return PDM_ERR_UNSUPPORTED;
     // (variant, cluster size): fewest waves first (a batch resident in ONE wave halves the time), then the on-chip map,
     // then the most CTAs per frame (fewer buckets per warp).  PDM_FPS_CLUSTER=<size> / PDM_FPS_CLUSTER_MAP=smem|global
     // force a choice (testing).
@@ -429,26 +442,32 @@ int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, floa
     const int forced = fe ? atoi(fe) : 0;
     const bool dbg = getenv("PDM_DEBUG_CLUSTER") != nullptr;
     int cl = 0, cap = 0, var = -1, best_waves = 1 << 30;
-    for (int v = 0; v < 2; ++v) {       // 0: map in shared memory, 1: map in global memory
-        if (me && ((me[0] == 's') != (v == 0))) continue;
-        const int vcap = v == 0 ? CbLS::CAP : CbLG::CAP;
-        for (int c = kCbMaxCl; c >= 2; --c) {
-            if (forced && c != forced) continue;
-            const int chunk = ((n + c - 1) / c + 31) / 32 * 32;
-            if (chunk > vcap) break;
-            if ((long long)(c - 1) * chunk >= n) continue;      // the last CTA would be empty
-            const int act = v == 0 ? cb_max_active_clusters(kern_s, 0, CbLS::kBytes, c) : cb_max_active_clusters(kern_g, 1, CbLG::kBytes, c);
-            if (dbg) fprintf(stderr, "[pdm]   cluster-bucket variant %d of %d: %d points per CTA, %d active clusters\n", v, c, chunk, act);
-            if (act < 1) continue;
-            const int waves = (b + act - 1) / act;
-            if (waves < best_waves) { best_waves = waves; cl = c; cap = chunk; var = v; }
+    for (int pass = 0; pass < 2; ++pass) {          // on-chip map first
+        for (int v = 0; v < kCbNumVariants; ++v) {
+            const CbVariant &V = kCbVariants[v];
+            if (V.smap != (pass == 0)) continue;
+            if (me && ((me[0] == 's') != V.smap)) continue;
+            for (int c = kCbMaxCl; c >= 2; --c) {
+                if (forced && c != forced) continue;
+                const int chunk = ((n + c - 1) / c + 31) / 32 * 32;
+                if (chunk > V.cap) break;
+                if (v > 0 && chunk <= kCbVariants[v - 1].cap && kCbVariants[v - 1].smap == V.smap) continue;   // a smaller variant holds it
+                if ((long long)(c - 1) * chunk >= n) continue;      // the last CTA would be empty
+                if (ensure_dynamic_smem((const void *)V.kern, V.smem) != PDM_OK) continue;
+                const int act = cb_max_active_clusters(v, c);
+                if (dbg) fprintf(stderr, "[pdm]   cluster-bucket variant %d of %d: %d points per CTA, %d active clusters\n", v, c, chunk, act);
+                if (act < 1) continue;
+                const int waves = (b + act - 1) / act;
+                if (waves < best_waves) { best_waves = waves; cl = c; cap = chunk; var = v; }
+            }
         }
     }
     if (cl == 0) return PDM_ERR_UNSUPPORTED;
+    const CbVariant &V = kCbVariants[var];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(b * cl));
     cfg.blockDim = dim3(kCbT);
-    cfg.dynamicSmemBytes = var == 0 ? CbLS::kBytes : CbLG::kBytes;
+    cfg.dynamicSmemBytes = V.smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -458,8 +477,7 @@ int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, floa
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (dbg) fprintf(stderr, "[pdm] fps cluster-bucket: b=%d n=%d variant=%d cl=%d chunk=%d waves=%d\n", b, n, var, cl, cap, best_waves);
-    const cudaError_t e = var == 0 ? cudaLaunchKernelEx(&cfg, kern_s, n, m, p, cap, xyz, temp, idx, stats)
-                                   : cudaLaunchKernelEx(&cfg, kern_g, n, m, p, cap, xyz, temp, idx, stats);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, V.kern, n, m, p, cap, xyz, temp, idx, stats);
     if (e != cudaSuccess) return fail((int)e, "farthest_point_sampling(cluster-bucket of %d): %s", cl, cudaGetErrorString(e));
     count_launch();
     return PDM_OK;

@@ -241,7 +241,8 @@ bool fps_cluster_supports(int n);
 
 
 // fps_cluster_bucket.cu: the same cluster layout with exact bucket pruning and multi-sample rounds (n <= 196608).
-int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st);
+int fps_cluster_bucket_launch(int b, int n, int m, int p, const float *xyz, float *temp, int *idx, int *stats, cudaStream_t st,
+                              bool small_ok = false);
 bool fps_cluster_bucket_supports(int n);
 
 }  // namespace pdm

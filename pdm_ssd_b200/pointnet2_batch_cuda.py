@@ -88,8 +88,13 @@ def ball_query_wrapper(b, n, m, radius, nsample, new_xyz_tensor, xyz_tensor, idx
     x = _chk(xyz_tensor, "xyz", _F32)
     i = _chk(idx_tensor, "idx", _I32)
     _need(new_xyz_tensor, "new_xyz", b * m * 3); _need(xyz_tensor, "xyz", b * n * 3); _need(idx_tensor, "idx", b * m * nsample)
+    mode = _lib.current_fps_mode()          # per-thread scheduling hint (`with _lib.fps_mode(...)`), passed per call
     with torch.cuda.device(xyz_tensor.device):
-        _lib.check(lib.pdm_ball_query(b, n, m, float(radius), nsample, q, x, i, _stream(xyz_tensor)), "ball_query")
+        if mode is None:
+            rc = lib.pdm_ball_query(b, n, m, float(radius), nsample, q, x, i, _stream(xyz_tensor))
+        else:
+            rc = lib.pdm_ball_query_ex(b, n, m, float(radius), nsample, q, x, i, mode, _stream(xyz_tensor))
+        _lib.check(rc, "ball_query")
     return 1
 
 
