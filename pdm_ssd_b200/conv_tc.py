@@ -70,8 +70,16 @@ def npad_of(cout):
     return 16 if cout <= 16 else 32 if cout <= 32 else 64 if cout <= 64 else 128
 
 
+def ncat_of(npad):
+    """Layers of at most 64 (padded) output channels use N-concatenated weight blocks (conv_tc.cu, ConvTCParams.ncat);
+    PDM_CONV_NCAT=0 switches that off on both sides (A/B measurements)."""
+    import os
+    return npad <= 64 and os.environ.get("PDM_CONV_NCAT", "1")[:1] != "0"
+
+
 def pack_conv_weight(w, b):
-    """w (Cout, Cin, k, k) fp32, b (Cout,) -> (bf16 blocks [Cin/32][k*k][hi|lo][4][npad][8], bias fp32 (npad,))."""
+    """w (Cout, Cin, k, k) fp32, b (Cout,) -> (bf16 blocks [Cin/32][k*k][hi|lo][4][npad][8] -- or, N-concatenated,
+    [Cin/32][k*k][4][hi|lo][npad][8] --, bias fp32 (npad,))."""
     cout, cin, k, k2 = w.shape
     if k != k2 or k not in (1, 3) or cin % 32 or cout > 128:
         raise RuntimeError("unsupported convolution shape %s for the tcgen05 path" % (tuple(w.shape),))
@@ -81,7 +89,10 @@ def pack_conv_weight(w, b):
     hi = wp.to(torch.bfloat16)
     lo = (wp - hi.float()).to(torch.bfloat16)
     planes = torch.stack([hi, lo]).reshape(2, npad, cin // 32, 4, 8, k * k)       # plane, n, kc, c8, e, tap
-    packed = planes.permute(2, 5, 0, 3, 1, 4).contiguous()                       # kc, tap, plane, c8, n, e
+    if ncat_of(npad):
+        packed = planes.permute(2, 5, 3, 0, 1, 4).contiguous()                   # kc, tap, c8, plane, n, e
+    else:
+        packed = planes.permute(2, 5, 0, 3, 1, 4).contiguous()                   # kc, tap, plane, c8, n, e
     bp = b.new_zeros(npad)
     bp[:cout] = b
     return packed, bp.contiguous()

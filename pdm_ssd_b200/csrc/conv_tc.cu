@@ -56,6 +56,11 @@ struct ConvTCParams {
     int w_resident;      // every weight block has its own slot: loaded once per CTA, never released
     int act;             // 0 none, 1 relu, 2 sigmoid
     int tmem_cols;
+    int ncat;            // N-concatenated weights (npad <= 64): blocks packed [chunk][hi|lo][n][8], so ONE MMA of N = 2 npad forms
+                         // A_hi x [W_hi; W_lo] in two column ranges of the accumulator (summed in the epilogue) and a second one of
+                         // N = npad adds A_lo x W_hi: 64 + 48 cycles per k-step instead of 3 x 48 (an N = 64 MMA is bound by the
+                         // 128 B/clk of shared-memory operand bandwidth, not by the tensor pipe)
+    int accw;            // TMEM columns per accumulator: npad, or 2 npad with ncat
     int debug;           // PDM_CONV_DEBUG (measurement only, results wrong): 1 halo loads only while the ring fills,
                          // 2 same for weight blocks, 4 no global stores in the epilogue
 };
@@ -186,14 +191,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
         // words never change).
         {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t idesc_cat = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * P.npad) >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t H16 = (uint32_t)P.halo * 16u;          // one chunk row of the halo tile
             const uint32_t a_lbo = H16, a_sbo = 4u * H16;
-            const uint32_t w_lbo = (uint32_t)P.npad * 16u;
+            const uint32_t w_lbo = (uint32_t)(P.ncat ? 2 * P.npad : P.npad) * 16u;     // one 8-channel chunk of a weight block
             const uint32_t a_hi_word = cv_desc_hi(a_sbo), w_hi_word = cv_desc_hi(128u);
             const uint32_t a_lbo_f = ((a_lbo >> 4) & 0x3fffu) << 16, w_lbo_f = ((w_lbo >> 4) & 0x3fffu) << 16;
             // descriptor low-word increments (units of 16 bytes)
             const uint32_t A_PLANE = (uint32_t)P.a_unit_bytes >> 4, A_UNIT = 2u * A_PLANE, A_KS = (2u * a_lbo) >> 4;
-            const uint32_t W_PLANE = (4u * w_lbo) >> 4, W_KS = (2u * w_lbo) >> 4, W_TAP = (uint32_t)P.w_block_bytes >> 4;
+            const uint32_t W_PLANE = (4u * w_lbo) >> 4, W_KS = (2u * w_lbo) >> 4, W_TAP = (uint32_t)P.w_block_bytes >> 4;   // (W_PLANE: !ncat)
+            const uint32_t ACCW = (uint32_t)P.accw;
             int as = 0, ws = 0; uint32_t aph = 0, wph = 0;
             for (int t = 0; t < n_tiles; ++t) {
                 const int nun = min(NU, u_last - (u_first + NU * t));
@@ -201,7 +208,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                 const uint32_t use = (uint32_t)(t >> 1);
                 mbar_wait(cv_smem_u32(&bars.acc_empty[set]), (use & 1u) ^ 1u, err, 103);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t acc0 = tmem_base + (uint32_t)(set * 2 * NU * P.npad);
+                const uint32_t acc0 = tmem_base + (uint32_t)(set * 2 * NU) * ACCW;
                 for (int kc = 0; kc < n_kc; ++kc) {
                     mbar_wait(cv_smem_u32(&bars.a_full[as]), aph, err, 104);
                     const uint32_t a_st = a_base + as * a_stage_bytes;
@@ -212,16 +219,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                         const uint32_t w_row = (((w_base + ws * (uint32_t)P.w_stage_bytes) >> 4) & 0x3fffu) | w_lbo_f;
                         const uint32_t first = (uint32_t)((kc | ky) != 0);
                         if (elect_one()) {
+                            if (P.ncat) {
+#pragma unroll 1
+                                for (int un = 0; un < nun; ++un) {
+                                    const uint32_t a_un = a_row + (uint32_t)un * A_UNIT;
+                                    const uint32_t d_un = acc0 + (uint32_t)(un * 2) * ACCW;
+#pragma unroll
+                                    for (int kx = 0; kx < 3; ++kx) {
+                                        if (kx < P.ksize) {
+#pragma unroll
+                                            for (int mh = 0; mh < 2; ++mh) {
+                                                const uint32_t d = d_un + (uint32_t)mh * ACCW;
+#pragma unroll
+                                                for (int ks = 0; ks < 2; ++ks) {
+                                                    const uint32_t ah = a_un + (uint32_t)(kx + 8 * mh) + (uint32_t)ks * A_KS;
+                                                    const uint32_t wh = w_row + (uint32_t)kx * W_TAP + (uint32_t)ks * W_KS;
+                                                    umma_bf16_lohi(d, ah, a_hi_word, wh, w_hi_word, idesc_cat, (kx | ks) ? 1u : first);   // A_hi x [W_hi; W_lo]
+                                                    umma_bf16_lohi(d, ah + A_PLANE, a_hi_word, wh, w_hi_word, idesc, 1u);                 // A_lo x W_hi
+                                                }
+                                            }
+                                        }
+                                    }
+                                }
+                            } else {
 #pragma unroll 1
                             for (int un = 0; un < nun; ++un) {
                                 const uint32_t a_un = a_row + (uint32_t)un * A_UNIT;
-                                const uint32_t d_un = acc0 + (uint32_t)(un * 2 * P.npad);
+                                const uint32_t d_un = acc0 + (uint32_t)(un * 2) * ACCW;
 #pragma unroll
                                 for (int kx = 0; kx < 3; ++kx) {
                                     if (kx < P.ksize) {
 #pragma unroll
                                         for (int mh = 0; mh < 2; ++mh) {
-                                            const uint32_t d = d_un + (uint32_t)(mh * P.npad);
+                                            const uint32_t d = d_un + (uint32_t)mh * ACCW;
 #pragma unroll
                                             for (int ks = 0; ks < 2; ++ks) {
                                                 const uint32_t ah = a_un + (uint32_t)(kx + 8 * mh) + (uint32_t)ks * A_KS;
@@ -233,6 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                                         }
                                     }
                                 }
+                            }
                             }
                             if (!P.w_resident) umma_commit(cv_smem_u32(&bars.w_empty[ws]));   // filter row free once these MMAs retire
                             if (ky + 1 == P.ksize) umma_commit(cv_smem_u32(&bars.a_empty[as]));   // halo chunk free
@@ -266,7 +297,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                 for (int mh = 0; mh < 2; ++mh) {
                     const int x = ux * 16 + mh * 8 + (lane & 7);
                     const bool valid = y < P.Y && x < P.X;
-                    const uint32_t col0 = (uint32_t)((set * 2 * NU + un * 2 + mh) * P.npad);
+                    const uint32_t col0 = (uint32_t)((set * 2 * NU + un * 2 + mh) * P.accw);
                     const size_t row0 = (((size_t)b * P.Y + y) * C8) * P.X + x;
 #pragma unroll 1
                     for (int ch = 0; ch * 32 < P.npad; ++ch) {
@@ -289,6 +320,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap_in, const ConvTCParams P
                             for (int j = 16; j < 32; ++j) v[j] = 0u;
                         }
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (P.ncat) {      // the A_hi x W_lo part sits npad columns further: add it
+                            uint32_t w2[32];
+                            if (P.npad >= 32) {
+                                tmem_ld_x32(taddr + (uint32_t)P.npad, w2);
+                            } else {
+                                asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                                             : "=r"(w2[0]), "=r"(w2[1]), "=r"(w2[2]), "=r"(w2[3]), "=r"(w2[4]), "=r"(w2[5]), "=r"(w2[6]), "=r"(w2[7]),
+                                               "=r"(w2[8]), "=r"(w2[9]), "=r"(w2[10]), "=r"(w2[11]), "=r"(w2[12]), "=r"(w2[13]), "=r"(w2[14]), "=r"(w2[15])
+                                             : "r"(taddr + (uint32_t)P.npad));
+                                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                                for (int j = 16; j < 32; ++j) w2[j] = 0u;
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__fadd_rn(__uint_as_float(v[j]), __uint_as_float(w2[j])));
+                        }
                         if (valid && !(P.debug & 4)) {
 #pragma unroll
                             for (int h = 0; h < 4; ++h) {
@@ -462,7 +509,10 @@ extern "C" int pdm_conv_tc_forward(int b, int y, int x, int cin, int cout, int k
     P.total_units = b * P.units_x * P.units_y;
     // two accumulator sets always (the epilogue of a tile overlaps the MMAs of the next): a tile is two 16x16 units
     // (4 accumulators) when 8 * npad TMEM columns fit, one unit otherwise
-    P.nu = 8 * P.npad <= 512 ? 2 : 1;
+    static const bool ncat_on = [] { const char *e = getenv("PDM_CONV_NCAT"); return !(e && e[0] == '0'); }();
+    P.ncat = (P.npad <= 64 && ncat_on) ? 1 : 0;      // the packing (conv_tc.py pack_conv_weight) follows the same rule
+    P.accw = P.ncat ? 2 * P.npad : P.npad;
+    P.nu = 8 * P.accw <= 512 ? 2 : 1;
     int per = (P.total_units + P.nu * kNumSMs - 1) / (P.nu * kNumSMs) * P.nu;
     if (per < P.nu) per = P.nu;
     P.units_per_cta = per;
@@ -470,7 +520,7 @@ extern "C" int pdm_conv_tc_forward(int b, int y, int x, int cin, int cout, int k
     P.a_unit_bytes = P.halo * 4 * P.halo * 16;
     P.w_block_bytes = 2 * 4 * P.npad * 16;
     P.w_stage_bytes = ksize * P.w_block_bytes;
-    int cols = 4 * P.nu * P.npad, pw = 32;
+    int cols = 4 * P.nu * P.accw, pw = 32;
     while (pw < cols) pw <<= 1;
     P.tmem_cols = pw;
     // shared memory: halo ring (2 stages when a tile has two units, else 3), the rest for filter rows (ksize weight
