@@ -156,7 +156,7 @@ int pdm_sa_fused_forward(int b, int n, int m, int c_feat, int nsample, int use_x
 /* pdm_sa_fused_forward with the optional operands of the faster kernels (all may be NULL):
  *   features_pm  the same features point-major (B, N, c_feat): the gather reads a row's channels from one place
  *   packed_tc3 / bias_tc3  operands of the persistent tcgen05 kernel (csrc/sa_tc.cu): per layer the BN-folded
- *                weights W'[n][k] as three bf16 planes hi|mid|lo (hi + mid + lo = w to 2^-24), each plane
+ *                weights W'[n][k] as two bf16 planes hi|lo (hi + lo = w to 2^-18), each plane
  *                [kpad/8][npad][8] with kpad, npad = widths rounded up to 16, layers back to back; bias fp32 [n_layers][128]
  *   out_pm       the result also written point-major (B, M, widths[n_layers]) -- what the next layer's gather and the
  *                detector's `point_features` (pointnet2_backbone.py:91-92) read

@@ -73,8 +73,8 @@ def _pack_folded_tc(folded):
 
 
 def _pack_folded_tc3(folded):
-    """Operands of the persistent tcgen05 kernel (csrc/sa_tc.cu): per layer the folded weights W'[n][k] as three
-    bf16 planes hi|mid|lo (hi + mid + lo = w to 2^-24), each plane [kpad/8][npad][8] with kpad, npad = widths rounded
+    """Operands of the persistent tcgen05 kernel (csrc/sa_tc.cu): per layer the folded weights W'[n][k] as two
+    bf16 planes hi|lo (hi + lo = w to 2^-18), each plane [kpad/8][npad][8] with kpad, npad = widths rounded
     up to 16 -- the K-major no-swizzle core-matrix layout, so a layer is one straight bulk copy into shared memory;
     bias fp32 (L, 128).  Returns (planes as a bf16 tensor, bias) or None when the stack does not fit the kernel."""
     if len(folded) < 2 or len(folded) > 3:
@@ -90,10 +90,8 @@ def _pack_folded_tc3(folded):
         wp[:n_out, :k_in] = w
         bias[l, :n_out] = b
         hi = wp.to(torch.bfloat16)
-        r1 = wp - hi.float()
-        mid = r1.to(torch.bfloat16)
-        lo = (r1 - mid.float()).to(torch.bfloat16)
-        planes = torch.stack([hi, mid, lo]).reshape(3, npad, kpad // 8, 8).permute(0, 2, 1, 3)     # plane, k8, n, 8
+        lo = (wp - hi.float()).to(torch.bfloat16)
+        planes = torch.stack([hi, lo]).reshape(2, npad, kpad // 8, 8).permute(0, 2, 1, 3)          # plane, k8, n, 8
         chunks.append(planes.reshape(-1))
     return torch.cat(chunks).contiguous(), bias.contiguous()
 

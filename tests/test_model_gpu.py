@@ -144,7 +144,10 @@ def test_fused_sa_scale_matches_unfused_path(N, M_, C, S, mlp, use_xyz, monkeypa
         nx2, ref = sa(xyz, feat)
     assert torch.equal(nx1, nx2) and fused.shape == ref.shape == (2, mlp[-1], M_)
     err = float((fused - ref).abs().max() / ref.abs().max().clamp_min(1e-12))
-    assert err < 1e-5, err          # budget of north_star: 1e-3 relative
+    # budget of north_star: 1e-3 relative.  The CUDA-core and thread-per-row kernels compute in fp32 (1e-5); the persistent
+    # tcgen05 kernel (the SA2 shape) carries fp32 as bf16 hi + lo pairs like the convolutions (tests/test_conv_gpu.py: 1e-4)
+    tc = S == 32 and 2 <= len(mlp) - 1 <= 3 and C + 3 * use_xyz > 8 and max(mlp[1:-1]) <= 64 and mlp[-1] <= 128
+    assert err < (1e-4 if tc else 1e-5), err
 
 
 def test_fused_path_is_skipped_when_it_must_be():

@@ -1,6 +1,6 @@
 """Fused SA scale, every kernel variant next to the unfused torch path (time after the ball query, batch 16):
    rows     thread-per-row kernel (narrow MLPs, csrc/sa_rows.cu)
-   tc3      persistent warp-specialised tcgen05 kernel, bf16 hi/mid/lo operands (csrc/sa_tc.cu)
+   tc3      persistent warp-specialised tcgen05 kernel, bf16 hi/lo operands, two tiles in flight (csrc/sa_tc.cu)
    tc_r1    round 1's tcgen05 kernel (tf32 hi/lo, one tile per CTA)
    cuda     CUDA-core kernel (sa_fused_kernel)
 """
