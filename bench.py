@@ -47,7 +47,8 @@ METRIC = "frames/s (full PDM-SSD inference, 16384-pt frames, batch 16 per GPU)" 
 WORKLOAD = ("configs[2]: full PDM-SSD KITTI 3-class inference (SA backbone 16384->4096->1024 + PDM neck + BEV context + "
             "hybrid heatmap/point head + rotated NMS), random-init weights, batch 16 per GPU; with N > 1 = configs[3]: frames "
             "sharded by rank, detections all-gathered over NCCL every step")
-STREAMS = int(os.environ.get("PDM_BENCH_STREAMS", "6"))        # batches in flight for the model
+STREAMS = int(os.environ.get("PDM_BENCH_STREAMS", "16"))       # batches in flight for the model (measured: 6 -> 7.80k, 8 -> 8.18k,
+                                                                # 12 -> 8.54k, 16 -> 8.66k, 24 -> 8.74k frames/s on one B200)
 SA_STREAMS = int(os.environ.get("PDM_BENCH_SA_STREAMS", "24"))  # for the SA-chain sub-record
 
 
@@ -183,6 +184,10 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # 16 slot streams + NCCL's stream on the default 8 hardware work queues alias each other: a 35 KB all-gather then waits
+    # behind whole forward graphs of unrelated slots (measured at 2 GPUs: 16.1k frames/s with 8 queues, 17.3k with 32; without
+    # any gather 17.5k).  Must be set before the CUDA context exists.
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     import torch
     import torch.distributed as dist
     from pdm_ssd_b200 import _lib
@@ -233,7 +238,7 @@ def main():
     host = [host_points(rank, s) for s in range(STREAMS)]
 
     # ---- device-resident throughput: STREAMS batches in flight, inputs resident in HBM ----------------------------
-    pipe = PipelinedDetector(model, BATCH, N_POINTS, STREAMS, dev, host=False, gather=world > 1)
+    pipe = PipelinedDetector(model, BATCH, N_POINTS, STREAMS, dev, host=False, gather=(world > 1 and not os.environ.get("PDM_BENCH_NO_GATHER")))
     pipe.capture([torch.from_numpy(h).to(dev) for h in host])
     pipelined(pipe, max(args.warmup, STREAMS))
     sampler = ClockSampler(local_rank)
@@ -243,11 +248,11 @@ def main():
     value = world * BATCH * args.steps / (ms_max * 1e-3)
     launches = pipe.launches_per_step * args.steps       # our kernels inside the replayed graphs
     det_shape = list(pipe.det[0].shape)
-    gathered_shape = list(pipe.gathered[0].shape) if world > 1 else None
+    gathered_shape = list(pipe.gathered[0].shape) if (world > 1 and pipe.gathered[0] is not None) else None
 
     # ---- end to end: pinned host points in, detections in pinned host memory out, copies inside every step --------
     pinned = [torch.from_numpy(h).pin_memory() for h in host]
-    hpipe = PipelinedDetector(model, BATCH, N_POINTS, STREAMS, dev, host=True, gather=world > 1)
+    hpipe = PipelinedDetector(model, BATCH, N_POINTS, STREAMS, dev, host=True, gather=(world > 1 and not os.environ.get("PDM_BENCH_NO_GATHER")))
     hpipe.capture(pinned)
     pipelined(hpipe, max(args.warmup, STREAMS))
     e2e_ms = timed(hpipe, args.steps)

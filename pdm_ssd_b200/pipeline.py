@@ -9,7 +9,9 @@ detections in pinned host memory, both copies inside the slot's graph -- the ser
 back, tools/eval_utils/eval_utils.py:58-79).  With `gather=True` (torch.distributed initialised) every step ends
 with the one collective of the sharded pipeline: an NCCL all-gather of the fixed-shape detections
 (`detector.gather_detections`, replacing the reference's pickle-file merge, pcdet/utils/common_utils.py:229-250),
-issued on the slot's stream right after the graph replay.
+issued on the slot's stream right after the graph replay.  With more than ~6 slots set CUDA_DEVICE_MAX_CONNECTIONS (hardware
+work queues, default 8) to at least n_streams + 2 before CUDA initialises: streams that alias one queue serialise, and the
+tiny all-gather then waits behind whole forward graphs of other slots (bench.py does this).
 """
 import torch
 

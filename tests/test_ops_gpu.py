@@ -207,9 +207,9 @@ def test_ball_query_golden(path):
 
 
 def test_ball_query_alternative_kernels_agree():
-    """The other kernels (PDM_BQ_KERNEL=bitmap: the shared-memory bitmap lookup, which also serves nsample > 64;
-    =tiled: reference-shaped scan) give the same rows as the default register top-k lookup.  Each variant runs in its
-    own interpreter."""
+    """Every lookup kernel forced on every shape (PDM_BQ_KERNEL=bitmap: shared-memory bitmaps, the default up to 32768
+    points and for nsample > 64; =topk: the register list, the default beyond; =tiled: reference-shaped scan) gives the
+    oracle's rows.  Each variant runs in its own interpreter."""
     import subprocess, sys
     code = (
         "import numpy as np, torch, sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
@@ -223,7 +223,7 @@ def test_ball_query_alternative_kernels_agree():
         "    ok = ok and np.array_equal(got, oracle.ball_query(r, s, fr, q))\n"
         "print('AGREE' if ok else 'DIFFER')"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
-    for variant in ("bitmap", "tiled"):
+    for variant in ("bitmap", "topk", "tiled"):
         env = dict(os.environ, PDM_BQ_KERNEL=variant)
         out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert out.returncode == 0, out.stderr[-2000:]

@@ -163,7 +163,7 @@ def test_vector_pool_family_vs_reference_golden(path):
 
 # ------------------------------------------------------------------------------------------------- oracle, seeded
 @pytest.mark.parametrize("counts,mcounts", [([900, 2100, 64], [100, 256, 64]), ([4096, 4096], [1024, 512]), ([1, 300], [1, 7]),
-                                            ([16384, 700], [512, 100])])
+                                            ([16384, 700], [512, 100]), ([30000, 9000], [300, 100])])   # last: register top-k lookup
 def test_fps_ball_query_group_vs_oracle(counts, mcounts):
     xyz, feat, cnt = ragged_cloud(counts, first_frame=31, dup_frame=0 if counts[0] > 1 and counts[0] < 5000 else None) \
         if max(counts) <= 4096 else (None, None, None)
