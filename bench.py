@@ -279,7 +279,15 @@ def main():
             model({"batch_size": BATCH, "points": dev_pts[i % 2]})
         l1.record()
         barrier()
-        latency_ms = reduce_max(l0.elapsed_time(l1)) / nlat
+        eager_ms = reduce_max(l0.elapsed_time(l1)) / nlat
+    # the same as ONE CUDA graph replayed on one stream (latency-mode sampling): what a batch alone costs on the GPU, without
+    # the host's ~70 eager launches per forward in the way (on a busy host the eager figure doubles, the graph one does not)
+    lpipe = PipelinedDetector(model, BATCH, N_POINTS, 1, dev, host=False, gather=False, fps_mode=_lib.FPS_MODE_LATENCY)
+    lpipe.capture([dev_pts[0]])
+    pipelined(lpipe, 3)
+    latency_ms = timed(lpipe, nlat) / nlat
+    del lpipe
+    with torch.no_grad():
         for i in range(5):
             bd = {"batch_size": BATCH, "points": dev_pts[i % 2], "pdm_fused_dense": True}
             for name, m in zip(names, model.module_list):
@@ -374,7 +382,9 @@ def main():
                    "l2": "per-step activations (BEV maps 4 x 288 MB) exceed the 126 MB L2; %d distinct input batches (one per slot)" % STREAMS},
         "roofline": roofline,
         "latency": {"ms_per_step_single_stream": latency_ms, "frames_per_s_single_stream": world * BATCH / (latency_ms * 1e-3),
-                    "what": "same forward, one batch alone on one stream, eager launches"},
+                    "eager_ms_per_step": eager_ms,
+                    "what": "same forward, one batch alone: one CUDA graph replayed on one stream, latency-mode sampling "
+                            "(eager_ms_per_step: the same with eager launches, host-dependent)"},
         "stage_ms": stage_ms,
         "e2e": e2e, "gpu_launches": int(launches), "gpu_launches_per_step": int(pipe.launches_per_step), "clocks": clocks,
     }

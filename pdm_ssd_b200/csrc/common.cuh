@@ -46,6 +46,16 @@ __device__ __forceinline__ float sqdist_ref(float dx, float dy, float dz) {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
 
+// Two fp32 multiply-adds in one instruction (fma.rn.f32x2 -> FFMA2 on sm_100a): c0 = a * b0 + c0, c1 = a * b1 + c1, each half
+// an IEEE fma (bit-identical to fmaf).  The CUDA-core MLP kernels (sa_rows.cu, point_head.cu) are bound by instruction ISSUE, not by the fp32 pipe: an FFMA2 takes one
+// issue slot for two pipe cycles, which frees the other slot for the LDS / index arithmetic around it.
+__device__ __forceinline__ void ffma2(float &c0, float &c1, float a, float b0, float b1) {
+    asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %2};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rc, {%0, %1};\n\t"
+        "fma.rn.f32x2 rc, ra, rb, rc;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+        : "+f"(c0), "+f"(c1) : "f"(a), "f"(b0), "f"(b1));
+}
+
+
 // fp32 carried as two bf16 values for the tensor-core layers (conv_tc.cu): hi = bf16(v), lo = bf16(v - hi);
 // hi + lo equals v to 2^-17 relative.
 __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {

@@ -102,9 +102,10 @@ point_head_kernel(PointHeadParams Q, const float *__restrict__ coords, const flo
             const float4 w4 = *reinterpret_cast<const float4 *>(Wb + c * kPHColBlock + ct * 4);
             const float av[4] = {a4.x, a4.y, a4.z, a4.w}, wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) acc[a][q] = fmaf(av[a], wv[q], acc[a][q]);
+            for (int a = 0; a < 4; ++a) {
+                ffma2(acc[a][0], acc[a][1], av[a], wv[0], wv[1]);
+                ffma2(acc[a][2], acc[a][3], av[a], wv[2], wv[3]);
+            }
         }
         if (ct * 4 < hn) {
 #pragma unroll

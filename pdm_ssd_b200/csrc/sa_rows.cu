@@ -40,10 +40,8 @@ __device__ __forceinline__ void rows_layer(const float (&in)[KIN], float (&acc)[
 #pragma unroll
         for (int j = 0; j < COUT; j += 4) {
             const float4 w4 = *reinterpret_cast<const float4 *>(w + k * COUT + j);
-            acc[j] = fmaf(a, w4.x, acc[j]);
-            acc[j + 1] = fmaf(a, w4.y, acc[j + 1]);
-            acc[j + 2] = fmaf(a, w4.z, acc[j + 2]);
-            acc[j + 3] = fmaf(a, w4.w, acc[j + 3]);
+            ffma2(acc[j], acc[j + 1], a, w4.x, w4.y);
+            ffma2(acc[j + 2], acc[j + 3], a, w4.z, w4.w);
         }
     }
 #pragma unroll
@@ -110,8 +108,8 @@ sa_rows_kernel(SARowsParams P, const float *__restrict__ xyz, const float *__res
                     const float a = lin[k];
                     const float4 wa = *reinterpret_cast<const float4 *>(w3 + k * COUT + j0);
                     const float4 wb = *reinterpret_cast<const float4 *>(w3 + k * COUT + j0 + 4);
-                    acc[0] = fmaf(a, wa.x, acc[0]); acc[1] = fmaf(a, wa.y, acc[1]); acc[2] = fmaf(a, wa.z, acc[2]); acc[3] = fmaf(a, wa.w, acc[3]);
-                    acc[4] = fmaf(a, wb.x, acc[4]); acc[5] = fmaf(a, wb.y, acc[5]); acc[6] = fmaf(a, wb.z, acc[6]); acc[7] = fmaf(a, wb.w, acc[7]);
+                    ffma2(acc[0], acc[1], a, wa.x, wa.y); ffma2(acc[2], acc[3], a, wa.z, wa.w);
+                    ffma2(acc[4], acc[5], a, wb.x, wb.y); ffma2(acc[6], acc[7], a, wb.z, wb.w);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
