@@ -48,6 +48,35 @@ __device__ __forceinline__ void rows_layer(const float (&in)[KIN], float (&acc)[
     for (int j = 0; j < COUT; ++j) acc[j] = fmaxf(acc[j], 0.f);
 }
 
+// the same for the TWO rows of a thread: every weight vector read from shared memory feeds both (ncu after the FFMA2 change:
+// short_scoreboard + mio_throttle on top -- the broadcast LDS.128 per two FFMA2 was the bottleneck)
+template <int KIN, int COUT>
+__device__ __forceinline__ void rows_layer2(const float (&in)[2][KIN], float (&acc)[2][COUT], const float *__restrict__ w,
+                                            const float *__restrict__ bias) {
+#pragma unroll
+    for (int j = 0; j < COUT; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(bias + j);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { acc[r][j] = b4.x; acc[r][j + 1] = b4.y; acc[r][j + 2] = b4.z; acc[r][j + 3] = b4.w; }
+    }
+#pragma unroll
+    for (int k = 0; k < KIN; ++k) {
+#pragma unroll
+        for (int j = 0; j < COUT; j += 4) {
+            const float4 w4 = *reinterpret_cast<const float4 *>(w + k * COUT + j);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                ffma2(acc[r][j], acc[r][j + 1], in[r][k], w4.x, w4.y);
+                ffma2(acc[r][j + 2], acc[r][j + 3], in[r][k], w4.z, w4.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int j = 0; j < COUT; ++j) acc[r][j] = fmaxf(acc[r][j], 0.f);
+}
+
 template <int K0, int C1, int C2, int C3>     // C3 == 0: two layers, C2 is the output width
 __global__ void __launch_bounds__(kRowsThreads)
 sa_rows_kernel(SARowsParams P, const float *__restrict__ xyz, const float *__restrict__ feats, const float *__restrict__ new_xyz,
@@ -56,7 +85,7 @@ sa_rows_kernel(SARowsParams P, const float *__restrict__ xyz, const float *__res
     constexpr int CLAST_IN = C3 > 0 ? C2 : C1;
     __shared__ __align__(16) float w1[K0 * C1], b1[C1], w2[C1 * C2], b2[C2];
     __shared__ __align__(16) float w3[C3 > 0 ? C2 * C3 : 4], b3[C3 > 0 ? C3 : 4];
-    __shared__ unsigned tile[COUT][kRowsThreads / 16 + 1];        // [channel][centre of this CTA iteration], bit patterns
+    __shared__ unsigned tile[COUT][2 * kRowsThreads / 16 + 1];    // [channel][centre of this CTA iteration], bit patterns
     const int tid = threadIdx.x, lane = tid & 31;
     // ---- weights -> shared memory (zero rows for the padded input channels) ---------------------------------------
     for (int t = tid; t < K0 * C1; t += kRowsThreads) w1[t] = (t / C1) < P.width0 ? __ldg(packed + P.woff[0] + t) : 0.f;
@@ -69,60 +98,72 @@ sa_rows_kernel(SARowsParams P, const float *__restrict__ xyz, const float *__res
     }
     __syncthreads();
     const int S = P.nsample;                      // 16 or 32
-    const int cpb = kRowsThreads / S;             // centres per CTA iteration
+    const int cph = kRowsThreads / S;             // centres per half of a CTA iteration
+    const int cpb = 2 * cph;                      // centres per CTA iteration: a thread owns one row of TWO centres
     const int total = P.b * P.m;
     const unsigned gmask = S == 32 ? 0xffffffffu : (0xffffu << (lane & 16));
     for (int g = blockIdx.x; g < P.groups; g += gridDim.x) {
         const int cl = tid / S, s = tid - cl * S;
-        const int ci = min(g * cpb + cl, total - 1);          // centres past the end are computed and dropped
-        const int bi = ci / P.m;
-        const int id = __ldg(idx + (size_t)ci * S + s);
-        float in[K0];
+        float in[2][K0];
 #pragma unroll
-        for (int k = 0; k < K0; ++k) in[k] = 0.f;
-        int c0 = 0;
-        if (P.use_xyz) {
-            const float *pp = xyz + ((size_t)bi * P.n + id) * 3;
-            const float *qq = new_xyz + (size_t)ci * 3;
+        for (int r = 0; r < 2; ++r) {
+            const int ci = min(g * cpb + r * cph + cl, total - 1);          // centres past the end are computed and dropped
+            const int bi = ci / P.m;
+            const int id = __ldg(idx + (size_t)ci * S + s);
 #pragma unroll
-            for (int a = 0; a < 3; ++a) in[a] = __fsub_rn(__ldg(pp + a), __ldg(qq + a));
-            c0 = 3;
+            for (int k = 0; k < K0; ++k) in[r][k] = 0.f;
+            int c0 = 0;
+            if (P.use_xyz) {
+                const float *pp = xyz + ((size_t)bi * P.n + id) * 3;
+                const float *qq = new_xyz + (size_t)ci * 3;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) in[r][a] = __fsub_rn(__ldg(pp + a), __ldg(qq + a));
+                c0 = 3;
+            }
+            const float *f = feats + (size_t)bi * P.c_feat * P.n + id;
+#pragma unroll
+            for (int k = 0; k < K0; ++k)
+                if (k >= c0 && k - c0 < P.c_feat) in[r][k] = __ldg(f + (size_t)(k - c0) * P.n);
         }
-        const float *f = feats + (size_t)bi * P.c_feat * P.n + id;
-#pragma unroll
-        for (int k = 0; k < K0; ++k)
-            if (k >= c0 && k - c0 < P.c_feat) in[k] = __ldg(f + (size_t)(k - c0) * P.n);
-        float a1[C1], a2[C2];
-        rows_layer<K0, C1>(in, a1, w1, b1);
-        rows_layer<C1, C2>(a1, a2, w2, b2);
+        float a1[2][C1], a2[2][C2];
+        rows_layer2<K0, C1>(in, a1, w1, b1);
+        rows_layer2<C1, C2>(a1, a2, w2, b2);
         // last layer in chunks of 8 output channels straight into the max-pool
-        const float(&lin)[CLAST_IN] = *reinterpret_cast<const float(*)[CLAST_IN]>(C3 > 0 ? a2 : a1);
         if (C3 > 0) {
 #pragma unroll
             for (int j0 = 0; j0 < COUT; j0 += 8) {
-                float acc[8];
+                float acc[2][8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = b3[j0 + j];
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[r][j] = b3[j0 + j];
 #pragma unroll
                 for (int k = 0; k < CLAST_IN; ++k) {
-                    const float a = lin[k];
                     const float4 wa = *reinterpret_cast<const float4 *>(w3 + k * COUT + j0);
                     const float4 wb = *reinterpret_cast<const float4 *>(w3 + k * COUT + j0 + 4);
-                    ffma2(acc[0], acc[1], a, wa.x, wa.y); ffma2(acc[2], acc[3], a, wa.z, wa.w);
-                    ffma2(acc[4], acc[5], a, wb.x, wb.y); ffma2(acc[6], acc[7], a, wb.z, wb.w);
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const float a = a2[r][k];
+                        ffma2(acc[r][0], acc[r][1], a, wa.x, wa.y); ffma2(acc[r][2], acc[r][3], a, wa.z, wa.w);
+                        ffma2(acc[r][4], acc[r][5], a, wb.x, wb.y); ffma2(acc[r][6], acc[r][7], a, wb.z, wb.w);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const unsigned mx = __reduce_max_sync(gmask, __float_as_uint(fmaxf(acc[j], 0.f)));
-                    if (s == 0) tile[j0 + j][cl] = mx;
-                }
+                for (int r = 0; r < 2; ++r)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const unsigned mx = __reduce_max_sync(gmask, __float_as_uint(fmaxf(acc[r][j], 0.f)));
+                        if (s == 0) tile[j0 + j][r * cph + cl] = mx;
+                    }
             }
         } else {
 #pragma unroll
-            for (int j = 0; j < COUT; ++j) {
-                const unsigned mx = __reduce_max_sync(gmask, __float_as_uint(a2[j]));
-                if (s == 0) tile[j][cl] = mx;
-            }
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+                for (int j = 0; j < COUT; ++j) {
+                    const unsigned mx = __reduce_max_sync(gmask, __float_as_uint(a2[r][j]));
+                    if (s == 0) tile[j][r * cph + cl] = mx;
+                }
         }
         __syncthreads();
         // ---- stores: (B, C_out, M) in runs of `cpb` consecutive centres per channel; optional point-major copy -----
@@ -169,7 +210,7 @@ int sa_rows_try(int b, int n, int m, int c_feat, int nsample, int use_xyz, const
         P.woff[l] = off; off += widths[l] * widths[l + 1];       // widths are multiples of 4: pad4(w) == w
         P.boff[l] = off; off += widths[l + 1];
     }
-    const int cpb = kRowsThreads / nsample;
+    const int cpb = 2 * kRowsThreads / nsample;      // a thread owns one row of two centres
     P.groups = (int)(((long long)b * m + cpb - 1) / cpb);
     const int k0 = widths[0] <= 4 ? 4 : 8, c1 = widths[1], c2 = widths[2], c3 = n_layers == 3 ? widths[3] : 0;
 #define PDM_ROWS(K0, C1, C2, C3) \
