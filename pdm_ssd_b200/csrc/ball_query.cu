@@ -27,14 +27,10 @@
 // points streamed through shared memory; identical results by construction.
 #include <stdlib.h>
 
-#include <cooperative_groups.h>
-
 #include <map>
 #include <mutex>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace pdm {
 
