@@ -276,42 +276,55 @@ static int stack_scatter_add_det(long long total, int per, int rows, int c, int 
 
 // ---------------------------------------------------------------------------------------------------------------
 // voxel query                                                                         (voxel_query_gpu.cu:10-88)
-// thread per centre walking the (2 z_range + 1)(2 y_range + 1)(2 x_range + 1) voxels around its own in the
-// reference's z, y, x order; a voxel holds one point index (or -1); keep the first nsample with d2 <= r^2.
+// the (2 z_range + 1)(2 y_range + 1)(2 x_range + 1) voxels around a centre's own in the reference's z, y, x order; a
+// voxel holds one point index (or -1); keep the first nsample with d2 <= r^2.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// One warp per centre: the lanes take 32 consecutive voxels of the neighbourhood in the reference's (z, y, x) loop order, a
+// ballot keeps the hits in that order (the reference walks up to (2 z_range + 1)(2 y_range + 1)(2 x_range + 1) voxels with one
+// thread: a chain of dependent loads).
+__global__ void __launch_bounds__(256)
 stack_voxel_query_kernel(int m, int r1, int r2, int r3, int nsample, float radius2, int z_range, int y_range, int x_range,
                          const float *__restrict__ new_xyz, const float *__restrict__ xyz, const int *__restrict__ new_coords,
                          const int *__restrict__ point_indices, int *__restrict__ idx) {
-    const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pt >= m) return;
     const float nx = __ldg(new_xyz + (size_t)pt * 3), ny = __ldg(new_xyz + (size_t)pt * 3 + 1), nz = __ldg(new_xyz + (size_t)pt * 3 + 2);
     const int4 co = __ldg(reinterpret_cast<const int4 *>(new_coords) + pt);   // [batch, z, y, x]
     int *row = idx + (size_t)pt * nsample;
-    int cnt = 0;
-    for (int dz = -z_range; dz <= z_range && cnt < nsample; ++dz) {
-        const int zc = co.y + dz;
-        if (zc < 0 || zc >= r1) continue;
-        for (int dy = -y_range; dy <= y_range && cnt < nsample; ++dy) {
-            const int yc = co.z + dy;
-            if (yc < 0 || yc >= r2) continue;
-            const size_t line = (((size_t)co.x * r1 + zc) * r2 + yc) * r3;
-            for (int dx = -x_range; dx <= x_range; ++dx) {
-                const int xc = co.w + dx;
-                if (xc < 0 || xc >= r3) continue;
-                const int k = __ldg(point_indices + line + xc);
-                if (k < 0) continue;
-                const float d2 = sqdist_ref(__fsub_rn(__ldg(xyz + (size_t)k * 3), nx), __fsub_rn(__ldg(xyz + (size_t)k * 3 + 1), ny),
-                                            __fsub_rn(__ldg(xyz + (size_t)k * 3 + 2), nz));
-                if (d2 > radius2) continue;
-                if (cnt == 0)
-                    for (int l = 1; l < nsample; ++l) row[l] = k;
-                row[cnt] = k;
-                if (++cnt >= nsample) break;    // the reference keeps walking only to count (cnt2, unused)
+    const int wy = 2 * y_range + 1, wx = 2 * x_range + 1;
+    const int total = (2 * z_range + 1) * wy * wx;
+    int cnt = 0, first = 0;
+    for (int base = 0; base < total && cnt < nsample; base += 32) {
+        const int v = base + lane;
+        int k = -1;
+        bool hit = false;
+        if (v < total) {
+            const int dz = v / (wy * wx) - z_range, rem = v % (wy * wx);
+            const int dy = rem / wx - y_range, dx = rem % wx - x_range;
+            const int zc = co.y + dz, yc = co.z + dy, xc = co.w + dx;
+            if (zc >= 0 && zc < r1 && yc >= 0 && yc < r2 && xc >= 0 && xc < r3) {
+                k = __ldg(point_indices + (((size_t)co.x * r1 + zc) * r2 + yc) * r3 + xc);
+                if (k >= 0) {
+                    const float d2 = sqdist_ref(__fsub_rn(__ldg(xyz + (size_t)k * 3), nx), __fsub_rn(__ldg(xyz + (size_t)k * 3 + 1), ny),
+                                                __fsub_rn(__ldg(xyz + (size_t)k * 3 + 2), nz));
+                    hit = !(d2 > radius2);
+                }
             }
         }
+        const unsigned ball = __ballot_sync(kAll, hit);
+        if (ball) {
+            if (cnt == 0) first = __shfl_sync(kAll, k, __ffs(ball) - 1);
+            const int slot = cnt + __popc(ball & ((1u << lane) - 1u));
+            if (hit && slot < nsample) row[slot] = k;
+            cnt += __popc(ball);
+        }
     }
-    if (cnt == 0) row[0] = -1;
+    if (cnt == 0) {
+        if (lane == 0) row[0] = -1;
+    } else {
+        for (int l = min(cnt, nsample) + lane; l < nsample; l += 32) row[l] = first;     // pad with the first hit
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -635,7 +648,7 @@ extern "C" int pdm_stack_voxel_query(int m, int r1, int r2, int r3, int nsample,
     PDM_NEG(m < 0 || r1 < 0 || r2 < 0 || r3 < 0 || nsample < 0 || z_range < 0 || y_range < 0 || x_range < 0, "stack_voxel_query");
     if (m == 0 || nsample == 0) return PDM_OK;
     if (!new_xyz || !xyz || !new_coords || !point_indices || !idx) return fail(PDM_ERR_INVALID_ARG, "stack_voxel_query: null pointer");
-    stack_voxel_query_kernel<<<(m + 127) / 128, 128, 0, (cudaStream_t)stream>>>(m, r1, r2, r3, nsample, radius * radius, z_range,
+    stack_voxel_query_kernel<<<(m + 7) / 8, 256, 0, (cudaStream_t)stream>>>(m, r1, r2, r3, nsample, radius * radius, z_range,
                                                                               y_range, x_range, new_xyz, xyz, new_coords,
                                                                               point_indices, idx);
     count_launch();
