@@ -18,11 +18,14 @@ Prints ONE JSON line (rank 0, last line of stdout).
              (`pipeline.PipelinedDetector`), CUDA events on the launch stream, max over ranks
   e2e        the same through the host API: every step starts from a PINNED HOST point cloud (H2D inside the step's
              graph) and ends with the detections in pinned host memory (D2H inside the step)
-  latency    one batch alone on one stream, eager launches
+  latency    one batch alone: ONE CUDA graph of the forward replayed on one stream, latency-mode sampling (the eager-launch
+             figure rides along)
   roofline   the kernel with the largest SM-time share of a step (tcgen05 convolution 128->128 of the BEV context
              block), timed alone with CUDA events: algorithmic fp32-conv FLOPs / time against the measured bf16 peak
-  stage_ms / kernels / sa_chain / neck_config0   sub-records (per-stage times, per-kernel achieved GB/s or TFLOP/s, the
-             set-abstraction op chain of configs[1] -- round 1's headline --, the neck alone at configs[0])
+  stage_ms / kernels / sa_chain / neck_config0 / waymo_config4 / stack_family   sub-records (per-stage times, per-kernel
+             achieved GB/s or TFLOP/s, the set-abstraction op chain of configs[1] -- round 1's headline --, the neck alone at
+             configs[0], the Waymo-scale chain of configs[4] -- at N > 1 on all GPUs at once --, the stacked operator family
+             next to the reference's own kernels)
   cpu_baseline   the same detector on this box's host cores (oracle/pdm_model_cpu.py: torch CPU modules + the C oracle
              for the CUDA-only ops), bounded sample
 `--impl reference` times that CPU arm alone with all host threads (BASELINE.json north_star prescribes it: the
@@ -402,6 +405,7 @@ def main():
         # the other BASELINE configs, each by its own tool in a child process (bounded; informational sub-records)
         line["neck_config0"] = tool_record("tools/bench_neck.py", [])                               # configs[0]
         line["waymo_config4"] = tool_record("tools/bench_waymo.py", ["--batch", "8", "--iters", "2"])   # configs[4], one GPU's share
+        line["stack_family"] = tool_record("tools/bench_stack.py", [])      # pointnet2_stack ops next to the reference's kernels
     if waymo_multi is not None:
         line["waymo_config4"] = waymo_multi
 
