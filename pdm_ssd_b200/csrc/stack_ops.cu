@@ -449,7 +449,6 @@ stack_vector_pool_kernel(int b, int m, const float *__restrict__ support_xyz, co
     const float *feat = support_features + (size_t)xstart * c_in;
     const float nx = __ldg(new_xyz + (size_t)pt * 3), ny = __ldg(new_xyz + (size_t)pt * 3 + 1), nz = __ldg(new_xyz + (size_t)pt * 3 + 2);
     const float r2 = __fmul_rn(dmax, dmax);
-    const int rounds = c_in / ceg;
     int sample_cnt = 0;
     bool stop = false;
     for (int base = 0; base < n && !stop; base += 32) {
@@ -522,11 +521,29 @@ stack_vector_pool_kernel(int b, int m, const float *__restrict__ support_xyz, co
             const float sx = __shfl_sync(kAll, lx, src), sy = __shfl_sync(kAll, ly, src), sz = __shfl_sync(kAll, lz, src);
             const float *frow = feat + (size_t)(base + src) * c_in;
             float *arow = acc + (size_t)sg * ceg;
-            for (int r = 0; r < rounds; ++r)
-                for (int j = lane; j < ceg; j += 32) {
-                    const float v = __ldg(frow + r * ceg + j);
-                    arow[j] = pooling_type == 0 ? __fadd_rn(arow[j], v) : v;
+            // channel i of the hit goes to slot i % ceg of its cell, in ascending i (the reference's serial loop).  One coalesced
+            // load of 32 channels per step; lanes < ceg own a slot and take the values of the lanes i = slot, slot + ceg, ...
+            // through shuffles, in that order (ceg >= 32: the 32 channels of a step fall into distinct slots).
+            for (int i0 = 0; i0 < c_in; i0 += 32) {
+                const int i = i0 + lane;
+                const float v = i < c_in ? __ldg(frow + i) : 0.f;
+                if (ceg >= 32) {
+                    if (i < c_in) { const int sl = i % ceg; arow[sl] = pooling_type == 0 ? __fadd_rn(arow[sl], v) : v; }
+                    __syncwarp();
+                } else {
+                    const int sl = (i0 + lane) % ceg;                    // slot of lane's channel; owner lanes: lane < ceg
+                    const int own = (i0 % ceg + lane) % ceg;             // slot owned by this lane in this step (lane < ceg)
+                    float a = lane < ceg ? arow[own] : 0.f;
+                    (void)sl;
+                    for (int q = 0; q * ceg < 32; ++q) {
+                        const int src = lane + q * ceg;                  // lane holding the q-th channel of my slot in this step
+                        const float o = __shfl_sync(kAll, v, src & 31);
+                        if (lane < ceg && src < 32 && i0 + src < c_in) a = pooling_type == 0 ? __fadd_rn(a, o) : o;
+                    }
+                    if (lane < ceg) arow[own] = a;
+                    __syncwarp();
                 }
+            }
             if (use_xyz && lane < 3) {
                 const float v = lane == 0 ? sx : (lane == 1 ? sy : sz);
                 lxyz[sg * 3 + lane] = pooling_type == 0 ? __fadd_rn(lxyz[sg * 3 + lane], v) : v;
