@@ -163,7 +163,7 @@ struct FpsSmem {
 // LB: thread count promised to ptxas.  The kernel always runs NW*32 threads; promising more makes ptxas
 // budget fewer registers per thread (65536 / LB), which leaves register-file room on the SM for
 // CTAs of OTHER kernels (ball query, grouping) next to a resident FPS CTA -- see fps_dispatch.
-template <int NW, int BPW, int KMAX, bool TRACE = false, int LB = NW * 32>
+template <int NW, int BPW, int KMAX, bool TRACE = false, int LB = NW * 32, bool PAIR = (BPW < 32)>
 __global__ void __launch_bounds__(LB, 1)
 fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__restrict__ temp,
                   int *__restrict__ idxs, int *__restrict__ stats, long long *__restrict__ trace = nullptr,
@@ -196,7 +196,9 @@ fps_bucket_kernel(int n, int m, int p, const float *__restrict__ xyz, float *__r
 
     if (tid == 0) out[0] = obase;
     if (m <= 1) return;
-    const bool pair = (rg.flags & 1) != 0;
+    // paired bucket updates: -2 % on frames of <= 8192 points, nothing at 16384 -- where the extra code costs registers
+    // (52 -> 112 bytes of spills at 96 registers, +3 %): compiled out for the 32-buckets-per-warp instantiation
+    const bool pair = PAIR && (rg.flags & 1) != 0;
 
     // ---- 1. frame bounding box ----------------------------------------------------------
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
