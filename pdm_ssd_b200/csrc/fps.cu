@@ -601,7 +601,7 @@ static int fps_dispatch(int b, int n, int m, const float *xyz, float *temp, int 
         // warps per CTA / samples per round: tuned on B200; PDM_FPS_NW / PDM_FPS_KMAX override
         const char *nwenv = getenv("PDM_FPS_NW"), *kenv = getenv("PDM_FPS_KMAX");
         const int nw = nwenv ? atoi(nwenv) : 16;
-        const int km = kenv ? atoi(kenv) : 8;
+        const int km = kenv ? atoi(kenv) : (n <= 8192 ? 12 : 8);      // measured: 12 is 2-3 % faster up to 8192 points, 8 at 16384
         if (n <= 1024) return launch_cap<1024>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
         if (n <= 2048) return launch_cap<2048>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
         if (n <= 4096) return launch_cap<4096>(nw, km, b, n, m, p, xyz, temp, idx, stats, st);
